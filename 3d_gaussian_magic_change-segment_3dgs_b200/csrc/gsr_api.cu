@@ -1,0 +1,449 @@
+// extern "C" entry points of libgsr (include/gsr.h) and the host-side orchestration of the stages.
+// Host logic mirrors CudaRasterizer::Rasterizer::forward/backward (cuda_rasterizer/rasterizer_impl.cu:198-458)
+// and the torch glue of rasterize_points.cu:35-242, without torch: raw device pointers + a stream.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "gsr_common.cuh"
+
+namespace gsr
+{
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return GSR_ERR_CUDA;
+}
+
+int after_launch(cudaStream_t s, bool debug, const char* stage)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) after stage '%s'", (int)e, cudaGetErrorString(e), stage);
+    return GSR_ERR_CUDA;
+}
+
+// ---- optional per-stage timing (bench.py roofline block) ----
+struct StageTimer
+{
+    bool enabled = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    float ms[GSR_STAGE_COUNT];
+    const char* out_names[GSR_STAGE_COUNT];
+    int count = 0;
+
+    void begin(cudaStream_t s)
+    {
+        names.clear();
+        if (!enabled) return;
+        mark(s, "start");
+    }
+    void mark(cudaStream_t s, const char* name)
+    {
+        if (!enabled) return;
+        if (names.size() >= ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        cudaEventRecord(ev[names.size()], s);
+        names.push_back(name);
+    }
+    void finish(cudaStream_t s, int first_slot)
+    {
+        if (!enabled || names.size() < 2) return;
+        cudaStreamSynchronize(s);
+        for (size_t i = 1; i < names.size() && first_slot + (int)i - 1 < GSR_STAGE_COUNT; i++) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev[i - 1], ev[i]);
+            ms[first_slot + i - 1] = t;
+            out_names[first_slot + i - 1] = names[i];
+            if (first_slot + (int)i > count) count = first_slot + (int)i;
+        }
+    }
+};
+static thread_local StageTimer g_timer;
+static const int kBwdFirstSlot = 10;
+
+static int ceil_log2(uint32_t v)
+{
+    int b = 0;
+    while (b < 32 && (1ull << b) < v) b++;
+    return b;
+}
+
+static int validate(const GsrView* view, const GsrGaussians* in)
+{
+    if (!view || !in) {
+        set_error("null view/gaussians");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (in->P < 0 || view->image_width <= 0 || view->image_height <= 0) {
+        set_error("invalid sizes P=%d W=%d H=%d", in->P, view->image_width, view->image_height);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (in->P == 0) return 0;
+    if (!in->means3D || !in->opacities || !view->bg || !view->viewmatrix || !view->projmatrix) {
+        set_error("means3D, opacities, bg, viewmatrix and projmatrix are required");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if ((in->shs == nullptr) == (in->colors_precomp == nullptr)) {
+        set_error("Please provide excatly one of either SHs or precomputed colors!");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    const bool sr = in->scales != nullptr && in->rotations != nullptr;
+    if (sr == (in->cov3D_precomp != nullptr) || ((in->scales != nullptr) != (in->rotations != nullptr))) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (in->shs) {
+        if (!view->campos) {
+            set_error("campos is required with SHs");
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+        const int need = (view->sh_degree + 1) * (view->sh_degree + 1);
+        if (view->sh_degree < 0 || view->sh_degree > 3 || view->sh_coeffs < need || view->sh_coeffs > 16) {
+            set_error("sh_degree=%d needs %d <= sh_coeffs <= 16, got %d", view->sh_degree, need, view->sh_coeffs);
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+    }
+    if (view->num_class != 0 && view->num_class != 2) {
+        set_error("num_class=%d is not built (the reference is compiled with NUM_CLASS=2; 0 disables segments)", view->num_class);
+        return GSR_ERR_UNSUPPORTED;
+    }
+    const int gx = (view->image_width + TILE_X - 1) / TILE_X, gy = (view->image_height + TILE_Y - 1) / TILE_Y;
+    if (gx > 65535 || gy > 65535) {
+        set_error("image too large: tile grid %dx%d exceeds 65535", gx, gy);
+        return GSR_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+} // namespace gsr
+
+using namespace gsr;
+
+extern "C" int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+extern "C" const char* gsr_last_error(void) { return g_err; }
+extern "C" void gsr_set_profiling(int enable) { g_timer.enabled = enable != 0; }
+extern "C" int gsr_get_stage_times(float* ms, const char** names)
+{
+    for (int i = 0; i < GSR_STAGE_COUNT; i++) {
+        ms[i] = i < g_timer.count ? g_timer.ms[i] : 0.f;
+        names[i] = i < g_timer.count && g_timer.out_names[i] ? g_timer.out_names[i] : "";
+    }
+    return g_timer.count;
+}
+
+extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const GsrOutputs* out, gsr_alloc_fn alloc, void* alloc_user,
+                           int32_t* num_rendered, gsr_stream_t stream_)
+{
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = validate(view, in);
+    if (rc) return rc;
+    if (num_rendered) *num_rendered = 0;
+    if (in->P == 0) return 0;
+    if (!out || !out->color || !out->depth || !out->alpha || !out->radii || (view->num_class == 2 && !out->segment) || !alloc) {
+        set_error("missing output pointers or allocator");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    const bool debug = view->debug != 0;
+    const int P = in->P, W = view->image_width, H = view->image_height;
+    const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+    const uint32_t T = (uint32_t)gx * (uint32_t)gy;
+    const size_t N = (size_t)W * H;
+
+    g_timer.count = 0;
+    g_timer.begin(s);
+
+    // ---- state buffers whose size is known up front ----
+    GeomState g;
+    const size_t geom_bytes = geom_layout(nullptr, P, g);
+    char* geom_base = (char*)alloc(alloc_user, GSR_BUF_GEOM, geom_bytes);
+    ImgState img;
+    const size_t img_bytes = img_layout(nullptr, N, T, img);
+    char* img_base = (char*)alloc(alloc_user, GSR_BUF_IMG, img_bytes);
+    if (!geom_base || !img_base) {
+        set_error("state allocation failed (geom %zu B, img %zu B)", geom_bytes, img_bytes);
+        return GSR_ERR_ALLOC;
+    }
+    geom_layout(geom_base, P, g);
+    img_layout(img_base, N, T, img);
+
+    GSR_CUDA(cudaMemsetAsync(g.counters, 0, CNT_WORDS * sizeof(uint32_t), s));
+
+    // ---- per-Gaussian preprocess ----
+    PreFwdArgs pa;
+    pa.P = P; pa.D = view->sh_degree; pa.M = in->shs ? view->sh_coeffs : 0; pa.S = in->segments ? view->num_class : 0;
+    pa.means3D = in->means3D; pa.scales = in->scales; pa.scale_modifier = view->scale_modifier; pa.rotations = in->rotations;
+    pa.opacities = in->opacities; pa.shs = in->shs; pa.cov3D_precomp = in->cov3D_precomp; pa.colors_precomp = in->colors_precomp;
+    pa.segments = in->segments; pa.view = view->viewmatrix; pa.proj = view->projmatrix; pa.campos = view->campos;
+    pa.W = W; pa.H = H; pa.tan_fovx = view->tanfovx; pa.tan_fovy = view->tanfovy;
+    pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:226-227
+    pa.focal_x = W / (2.0f * view->tanfovx);
+    pa.grid_x = gx; pa.grid_y = gy; pa.prefiltered = view->prefiltered; pa.radii = out->radii; pa.g = g;
+    launch_preprocess_fwd(pa, s);
+    GSR_LAUNCHED(s, debug, "preprocess_fwd");
+    launch_block_offsets(g, s);
+    GSR_LAUNCHED(s, debug, "block_offsets");
+    g_timer.mark(s, "preprocess_fwd");
+
+    // ---- the one host synchronisation: V and R size the binning state (reference: rasterizer_impl.cu:285) ----
+    uint32_t counters[8];
+    GSR_CUDA(cudaMemcpyAsync(counters, g.counters, sizeof(counters), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaStreamSynchronize(s));
+    if (counters[CNT_ERROR] & 1u) {
+        set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
+        return GSR_ERR_PREFILTERED;
+    }
+    const uint32_t V = counters[CNT_VISIBLE];
+    const unsigned long long R64 = (unsigned long long)counters[CNT_RENDERED_LO] | ((unsigned long long)counters[CNT_RENDERED_LO + 1] << 32);
+    if (R64 > 0x7fffffffull) {
+        set_error("%llu tile instances exceed the int32 limit", R64);
+        return GSR_ERR_OVERFLOW;
+    }
+    const uint32_t R = (uint32_t)R64;
+    if (num_rendered) *num_rendered = (int32_t)R;
+
+    BinState b;
+    const size_t bin_bytes = bin_layout(nullptr, V, R, b);
+    char* bin_base = (char*)alloc(alloc_user, GSR_BUF_BINNING, bin_bytes);
+    if (!bin_base) {
+        set_error("binning state allocation failed (%zu B)", bin_bytes);
+        return GSR_ERR_ALLOC;
+    }
+    bin_layout(bin_base, V, R, b);
+
+    // ---- depth order of the visible Gaussians ----
+    launch_depth_keys(g, b, s);
+    GSR_LAUNCHED(s, debug, "depth_keys");
+    int dres = radix_sort_pairs(b.dkeys, b.dvals, V, 32, b.hist, b.hist_words, s);
+    if (dres < 0) return dres;
+    GSR_LAUNCHED(s, debug, "depth_sort");
+    const uint32_t* sorted_slots = b.dvals[dres];
+    g_timer.mark(s, "depth_sort");
+
+    // ---- instances in depth order, then stable sort by tile ----
+    rc = launch_instance_offsets(g, b, V, sorted_slots, s);
+    if (rc) return rc;
+    GSR_LAUNCHED(s, debug, "instance_offsets");
+    const int tile_bits = ceil_log2(T) < 1 ? 1 : ceil_log2(T);
+    const int tpasses = radix_num_passes(tile_bits);
+    // choose the starting buffers so that the final pass lands in point_list (offset 0 of the binning state)
+    uint32_t* tvals[2];
+    uint32_t* tkeys[2] = {b.tkeys[0], b.tkeys[1]};
+    if (tpasses % 2 == 0) { tvals[0] = b.point_list; tvals[1] = b.vals_alt; }
+    else { tvals[0] = b.vals_alt; tvals[1] = b.point_list; }
+    rc = launch_emit(g, b, V, R, sorted_slots, gx, tkeys[0], tvals[0], s);
+    if (rc) return rc;
+    GSR_LAUNCHED(s, debug, "emit");
+    g_timer.mark(s, "emit");
+    int tres = radix_sort_pairs(tkeys, tvals, R, tile_bits, b.hist, b.hist_words, s);
+    if (tres < 0) return tres;
+    GSR_LAUNCHED(s, debug, "tile_sort");
+    if (R > 0 && tvals[tres] != b.point_list) {
+        set_error("internal: tile sort ended in the wrong buffer");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    g_timer.mark(s, "tile_sort");
+    rc = launch_tile_ranges(tkeys[tres], R, img.ranges, T, s);
+    if (rc) return rc;
+    GSR_LAUNCHED(s, debug, "tile_ranges");
+    g_timer.mark(s, "tile_ranges");
+
+    // ---- compositing ----
+    RenderArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.W = W; ra.H = H; ra.grid_x = gx; ra.grid_y = gy;
+    ra.ranges = img.ranges; ra.point_list = b.point_list; ra.rec = g.rec; ra.bg = view->bg;
+    ra.out_color = out->color; ra.out_segment = out->segment; ra.out_depth = out->depth; ra.out_alpha = out->alpha;
+    ra.n_contrib = img.n_contrib;
+    launch_render_fwd(ra, view->num_class, s);
+    GSR_LAUNCHED(s, debug, "render_fwd");
+    g_timer.mark(s, "render_fwd");
+    g_timer.finish(s, 0);
+    return 0;
+}
+
+extern "C" size_t gsr_backward_scratch_bytes(int32_t P)
+{
+    if (P <= 0) return 0;
+    const size_t nblk = ((size_t)P + PRE_BLOCK - 1) / PRE_BLOCK;
+    return nblk * PRE_BLOCK * GRAD_REC_FLOATS * sizeof(float) + 256;
+}
+
+extern "C" int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
+                            const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, gsr_stream_t stream_)
+{
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = validate(view, in);
+    if (rc) return rc;
+    if (in->P == 0) return 0;
+    if (!radii || !state || !state->geom || !state->img || !alpha || !pix || !pix->dL_dcolor || !grads || !scratch) {
+        set_error("gsr_backward: missing argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (state->num_rendered > 0 && !state->binning) {
+        set_error("gsr_backward: binning state missing");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (scratch_bytes < gsr_backward_scratch_bytes(in->P)) {
+        set_error("gsr_backward: scratch too small (%zu < %zu)", scratch_bytes, gsr_backward_scratch_bytes(in->P));
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    const bool debug = view->debug != 0;
+    const int P = in->P, W = view->image_width, H = view->image_height;
+    const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+    const uint32_t T = (uint32_t)gx * (uint32_t)gy;
+
+    GeomState g;
+    geom_layout((char*)state->geom, P, g);
+    ImgState img;
+    img_layout((char*)state->img, (size_t)W * H, T, img);
+    float* grad_rec = (float*)align_up((size_t)scratch, 256);
+
+    g_timer.begin(s);
+    GSR_CUDA(cudaMemsetAsync(grad_rec, 0, (size_t)g.slots * GRAD_REC_FLOATS * sizeof(float), s));
+
+    RenderArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.W = W; ra.H = H; ra.grid_x = gx; ra.grid_y = gy;
+    ra.ranges = img.ranges; ra.point_list = (const uint32_t*)state->binning; ra.rec = g.rec; ra.bg = view->bg;
+    ra.n_contrib = img.n_contrib; ra.alphas = alpha;
+    ra.dL_dcolor = pix->dL_dcolor; ra.dL_dsegment = pix->dL_dsegment; ra.dL_ddepth = pix->dL_ddepth; ra.dL_dalpha = pix->dL_dalpha;
+    ra.grad_rec = grad_rec;
+    launch_render_bwd(ra, view->num_class, s);
+    GSR_LAUNCHED(s, debug, "render_bwd");
+    g_timer.mark(s, "render_bwd");
+
+    PreBwdArgs pb;
+    pb.P = P; pb.D = view->sh_degree; pb.M = in->shs ? view->sh_coeffs : 0; pb.S = view->num_class;
+    pb.means3D = in->means3D; pb.scales = in->scales; pb.scale_modifier = view->scale_modifier; pb.rotations = in->rotations;
+    pb.shs = in->shs; pb.cov3D_precomp = in->cov3D_precomp; pb.view = view->viewmatrix; pb.proj = view->projmatrix; pb.campos = view->campos;
+    pb.W = W; pb.H = H; pb.tan_fovx = view->tanfovx; pb.tan_fovy = view->tanfovy;
+    pb.focal_y = H / (2.0f * view->tanfovy);
+    pb.focal_x = W / (2.0f * view->tanfovx);
+    pb.radii = radii; pb.g = g; pb.grad_rec = grad_rec; pb.out = *grads;
+    pb.colors_precomp_given = in->colors_precomp != nullptr;
+    if (!in->shs) pb.out.dL_dsh = nullptr;
+    if (!in->scales) { pb.out.dL_dscales = nullptr; pb.out.dL_drotations = nullptr; }
+    launch_preprocess_bwd(pb, s);
+    GSR_LAUNCHED(s, debug, "preprocess_bwd");
+    g_timer.mark(s, "preprocess_bwd");
+    g_timer.finish(s, kBwdFirstSlot);
+    return 0;
+}
+
+extern "C" int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                                gsr_stream_t stream_)
+{
+    (void)projmatrix; // the reference computes the projected point but only tests view-space z (auxiliary.h:154)
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+        set_error("gsr_mark_visible: invalid argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream_);
+    GSR_LAUNCHED((cudaStream_t)stream_, false, "mark_visible");
+    return 0;
+}
+
+extern "C" size_t gsr_knn_workspace_bytes(int32_t P) { return knn_workspace_bytes(P); }
+
+extern "C" int gsr_knn_dist2(int32_t P, const float* points, float* mean_dist2, void* workspace, size_t workspace_bytes, gsr_stream_t stream_)
+{
+    if (P < 0 || (P > 0 && (!points || !mean_dist2 || !workspace))) {
+        set_error("gsr_knn_dist2: invalid argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (P == 0) return 0;
+    if (workspace_bytes < knn_workspace_bytes(P)) {
+        set_error("gsr_knn_dist2: workspace too small");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    return knn_run(P, points, mean_dist2, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+// ------------------------------------------------------------------------------------------ state export
+namespace gsr
+{
+__global__ void export_gaussians_kernel(GeomState g, uint32_t nslots_blocks, GsrStateExport o)
+{
+    const uint32_t b = blockIdx.x;
+    const uint32_t cnt = g.blk_count[b];
+    if (threadIdx.x >= cnt) return;
+    const uint32_t slot = b * PRE_BLOCK + threadIdx.x;
+    const uint32_t id = g.slot_gid[slot];
+    const float4 A = g.rec[3 * (size_t)slot], B = g.rec[3 * (size_t)slot + 1], C = g.rec[3 * (size_t)slot + 2];
+    if (o.depths) o.depths[id] = C.y;
+    if (o.means2D) { o.means2D[2 * (size_t)id] = A.x; o.means2D[2 * (size_t)id + 1] = A.y; }
+    if (o.conic_opacity) {
+        o.conic_opacity[4 * (size_t)id + 0] = A.z; o.conic_opacity[4 * (size_t)id + 1] = A.w;
+        o.conic_opacity[4 * (size_t)id + 2] = B.x; o.conic_opacity[4 * (size_t)id + 3] = B.y;
+    }
+    if (o.rgb) { o.rgb[3 * (size_t)id] = B.z; o.rgb[3 * (size_t)id + 1] = B.w; o.rgb[3 * (size_t)id + 2] = C.x; }
+    if (o.clamped) {
+        const uint8_t cb = g.clamped[slot];
+        o.clamped[3 * (size_t)id] = cb & 1; o.clamped[3 * (size_t)id + 1] = (cb >> 1) & 1; o.clamped[3 * (size_t)id + 2] = (cb >> 2) & 1;
+    }
+    if (o.tiles_touched) {
+        const ushort4 r = g.rect[slot];
+        o.tiles_touched[id] = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
+    }
+}
+
+__global__ void export_lists_kernel(GeomState g, const uint32_t* point_list, const uint2* ranges, uint32_t T, GsrStateExport o)
+{
+    // one CTA per tile: its range of the sorted list
+    const uint32_t t = blockIdx.x;
+    if (t >= T) return;
+    const uint2 r = ranges[t];
+    for (uint32_t k = r.x + threadIdx.x; k < r.y; k += blockDim.x) {
+        const uint32_t slot = point_list[k];
+        if (o.point_list) o.point_list[k] = g.slot_gid[slot];
+        if (o.point_keys) o.point_keys[k] = ((uint64_t)t << 32) | (uint64_t)__float_as_uint(g.rec[3 * (size_t)slot + 2].y);
+    }
+}
+} // namespace gsr
+
+extern "C" int gsr_export_state(int32_t P, int32_t W, int32_t H, const GsrState* state, const GsrStateExport* out, gsr_stream_t stream_)
+{
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (P <= 0 || !state || !out || !state->geom || !state->img) {
+        set_error("gsr_export_state: invalid argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+    const uint32_t T = (uint32_t)gx * (uint32_t)gy;
+    const size_t N = (size_t)W * H;
+    GeomState g;
+    geom_layout((char*)state->geom, P, g);
+    ImgState img;
+    img_layout((char*)state->img, N, T, img);
+    if (out->depths) GSR_CUDA(cudaMemsetAsync(out->depths, 0, (size_t)P * 4, s));
+    if (out->means2D) GSR_CUDA(cudaMemsetAsync(out->means2D, 0, (size_t)P * 8, s));
+    if (out->conic_opacity) GSR_CUDA(cudaMemsetAsync(out->conic_opacity, 0, (size_t)P * 16, s));
+    if (out->rgb) GSR_CUDA(cudaMemsetAsync(out->rgb, 0, (size_t)P * 12, s));
+    if (out->clamped) GSR_CUDA(cudaMemsetAsync(out->clamped, 0, (size_t)P * 3, s));
+    if (out->tiles_touched) GSR_CUDA(cudaMemsetAsync(out->tiles_touched, 0, (size_t)P * 4, s));
+    export_gaussians_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, g.nblk, *out);
+    GSR_LAUNCHED(s, false, "export_gaussians");
+    if ((out->point_list || out->point_keys) && state->num_rendered > 0) {
+        export_lists_kernel<<<T, 256, 0, s>>>(g, (const uint32_t*)state->binning, img.ranges, T, *out);
+        GSR_LAUNCHED(s, false, "export_lists");
+    }
+    if (out->ranges) GSR_CUDA(cudaMemcpyAsync(out->ranges, img.ranges, (size_t)T * 8, cudaMemcpyDeviceToDevice, s));
+    if (out->n_contrib) GSR_CUDA(cudaMemcpyAsync(out->n_contrib, img.n_contrib, N * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}

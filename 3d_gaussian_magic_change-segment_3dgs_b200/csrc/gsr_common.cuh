@@ -1,0 +1,225 @@
+// Shared declarations of libgsr: state layouts, launch-side structs, error helpers.
+// sm_100a only. No torch types anywhere below the C ABI (include/gsr.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gsr.h"
+
+namespace gsr
+{
+constexpr int TILE_X = 16;            // reference BLOCK_X / BLOCK_Y (cuda_rasterizer/config.h:17-18)
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIXELS = TILE_X * TILE_Y;
+constexpr int PRE_BLOCK = 256;        // Gaussians per preprocess CTA == slots per slot-block
+constexpr int GRAD_REC_FLOATS = 12;   // per-Gaussian record accumulated by the compositing backward
+
+// ---- header counters at the start of the geometry state ----
+enum { CNT_VISIBLE = 0, CNT_RENDERED_LO = 2, CNT_ERROR = 4, CNT_WORDS = 64 };
+
+// Per-visible-Gaussian record, 48 B, in a "slot": slot = block*256 + rank of the Gaussian among the visible
+// ones of its preprocess block. Slots of a block are contiguous, so the state stays dense in 128-B lines
+// without a global compaction pass. Fields (what the reference keeps as means2D/conic_opacity/rgb/depths):
+//   A = { mean2D.x, mean2D.y, conic.x, conic.y }
+//   B = { conic.z,  opacity,  rgb.r,   rgb.g   }
+//   C = { rgb.b,    depth,    seg0,    seg1    }
+struct GeomState
+{
+    uint32_t* counters;  // [CNT_WORDS]
+    float4* rec;         // [3 * slots]
+    ushort4* rect;       // [slots] tile rectangle {xmin, ymin, xmax, ymax} (auxiliary.h:46-56)
+    uint32_t* slot_gid;  // [slots] Gaussian id of the slot
+    uint8_t* clamped;    // [slots] bit c set <=> SH colour channel c was clamped (forward.cu:67-69)
+    uint32_t* blk_count; // [nblk] visible Gaussians per slot-block
+    uint32_t* blk_offset;// [nblk] exclusive scan of blk_count
+    uint32_t nblk;
+    uint32_t slots;      // nblk * PRE_BLOCK
+};
+
+struct BinState
+{
+    uint32_t* point_list; // [R] final per-tile lists (slots), depth-sorted; MUST be first (gsr_backward relies on offset 0)
+    uint32_t* vals_alt;   // [R]
+    uint32_t* tkeys[2];   // [R] tile ids (ping-pong)
+    uint32_t* dkeys[2];   // [V] depth bits (ping-pong)
+    uint32_t* dvals[2];   // [V] slots (ping-pong)
+    uint32_t* soff;       // [V+1] exclusive scan of tiles_touched in depth order
+    uint32_t* hist;       // radix block histograms followed by their scan partials
+    size_t hist_words;
+    uint32_t* scan_part;  // partials of the instance-offset scan
+};
+
+struct ImgState
+{
+    uint32_t* n_contrib; // [H*W]
+    uint2* ranges;       // [T]
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+inline void carve(char*& p, T*& out, size_t count)
+{
+    p = (char*)align_up((size_t)p, 256);
+    out = (T*)p;
+    p += count * sizeof(T);
+}
+
+inline size_t geom_layout(char* base, int P, GeomState& g)
+{
+    char* p = base;
+    g.nblk = (uint32_t)((P + PRE_BLOCK - 1) / PRE_BLOCK);
+    g.slots = g.nblk * PRE_BLOCK;
+    carve(p, g.counters, (size_t)CNT_WORDS);
+    carve(p, g.rec, (size_t)3 * g.slots);
+    carve(p, g.rect, (size_t)g.slots);
+    carve(p, g.slot_gid, (size_t)g.slots);
+    carve(p, g.clamped, (size_t)g.slots);
+    carve(p, g.blk_count, (size_t)g.nblk);
+    carve(p, g.blk_offset, (size_t)g.nblk + 1);
+    return (size_t)(p - base) + 256;
+}
+
+constexpr int RADIX_ITEMS = 4096;  // keys per radix CTA (256 threads x 16)
+constexpr int SCAN_ITEMS = 2048;   // items per scan CTA (256 threads x 8)
+
+inline size_t bin_layout(char* base, size_t V, size_t R, BinState& b)
+{
+    char* p = base;
+    carve(p, b.point_list, R);
+    carve(p, b.vals_alt, R);
+    carve(p, b.tkeys[0], R);
+    carve(p, b.tkeys[1], R);
+    carve(p, b.dkeys[0], V);
+    carve(p, b.dkeys[1], V);
+    carve(p, b.dvals[0], V);
+    carve(p, b.dvals[1], V);
+    carve(p, b.soff, V + 1);
+    size_t n = R > V ? R : V;
+    size_t nb = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    size_t h = 256 * (nb + 1);
+    b.hist_words = h + (h + SCAN_ITEMS - 1) / SCAN_ITEMS + 64;
+    carve(p, b.hist, b.hist_words);
+    carve(p, b.scan_part, (V + SCAN_ITEMS) / SCAN_ITEMS + 64);
+    return (size_t)(p - base) + 256;
+}
+
+inline size_t img_layout(char* base, size_t N, size_t T, ImgState& s)
+{
+    char* p = base;
+    carve(p, s.n_contrib, N);
+    carve(p, s.ranges, T);
+    return (size_t)(p - base) + 256;
+}
+
+// ---- error plumbing (thread-local message, C-ABI return codes) ----
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define GSR_CUDA(call)                                      \
+    do {                                                    \
+        int _rc = gsr::check_cuda((call), #call);           \
+        if (_rc) return _rc;                                \
+    } while (0)
+
+// After a kernel launch: always catch launch-configuration errors; in debug mode also synchronise
+// (the reference's CHECK_CUDA, auxiliary.h:166-173).
+int after_launch(cudaStream_t s, bool debug, const char* stage);
+#define GSR_LAUNCHED(stream, debug, stage)                           \
+    do {                                                             \
+        int _rc = gsr::after_launch((stream), (debug), (stage));     \
+        if (_rc) return _rc;                                         \
+    } while (0)
+
+// ---- launch-side argument blocks ----
+struct PreFwdArgs
+{
+    int P, D, M, S;
+    const float* means3D;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* colors_precomp;
+    const float* segments;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    int W, H;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    int grid_x, grid_y;
+    int prefiltered;
+    int32_t* radii;
+    GeomState g;
+};
+
+struct PreBwdArgs
+{
+    int P, D, M, S;
+    const float* means3D;
+    const float* scales;
+    float scale_modifier;
+    const float* rotations;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    int W, H;
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    const int32_t* radii;
+    GeomState g;
+    const float* grad_rec; // [slots][12]
+    GsrParamGrads out;
+    bool colors_precomp_given;
+};
+
+struct RenderArgs
+{
+    int W, H, grid_x, grid_y;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float4* rec;
+    const float* bg;
+    // forward outputs
+    float* out_color;
+    float* out_segment;
+    float* out_depth;
+    float* out_alpha;
+    uint32_t* n_contrib;
+    // backward inputs
+    const float* alphas;
+    const float* dL_dcolor;
+    const float* dL_dsegment;
+    const float* dL_ddepth;
+    const float* dL_dalpha;
+    float* grad_rec;
+};
+
+// ---- stage launchers (each defined next to its kernels) ----
+int launch_preprocess_fwd(const PreFwdArgs& a, cudaStream_t s);
+int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
+int launch_block_offsets(const GeomState& g, cudaStream_t s);
+int launch_depth_keys(const GeomState& g, const BinState& b, cudaStream_t s);
+int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, const uint32_t* sorted_slots, cudaStream_t s);
+int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, int grid_x,
+                uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s);
+int launch_tile_ranges(const uint32_t* sorted_tile_keys, uint32_t R, uint2* ranges, uint32_t T, cudaStream_t s);
+int launch_render_fwd(const RenderArgs& a, int S, cudaStream_t s);
+int launch_render_bwd(const RenderArgs& a, int S, cudaStream_t s);
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
+
+// exclusive scan of n u32 values (in may alias out); writes the grand total to out[n] when write_total.
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, bool write_total, uint32_t* partials, cudaStream_t s);
+// stable LSD radix sort of (key,val) pairs on key bits [0,nbits). Result lands in keys[res]/vals[res]; returns res (0/1) or <0.
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* hist, size_t hist_words, cudaStream_t s);
+int radix_num_passes(int nbits);
+
+int knn_run(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t knn_workspace_bytes(int P);
+
+} // namespace gsr

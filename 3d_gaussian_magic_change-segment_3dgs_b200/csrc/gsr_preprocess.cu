@@ -1,0 +1,420 @@
+// Per-Gaussian stages: forward preprocess (cull, EWA projection, SH colour, tile rectangle, slot compaction),
+// backward preprocess (conic/cov2D, projection, depth, SH and scale/rotation gradients, dense gradient rows),
+// and the frustum mark.
+//
+// Replaces the reference kernels preprocessCUDA (forward.cu:155-256), computeCov2DCUDA + preprocessCUDA
+// (backward.cu:144-274, 346-412) and checkFrustum (rasterizer_impl.cu:54-66), plus the 11 zero-fills of
+// rasterize_points.cu:166-177 (every gradient row is written exactly once here).
+#include "gsr_math.cuh"
+
+namespace gsr
+{
+namespace
+{
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Exclusive prefix of `flag` over the 256-thread block (thread order) + block total.
+__device__ __forceinline__ uint32_t block_rank_256(bool flag, uint32_t* s_warp /*[8]*/, uint32_t& total)
+{
+    const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+    const uint32_t warp = threadIdx.x >> 5;
+    if (lane_id() == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) base += c;
+        tot += c;
+    }
+    total = tot;
+    return base + __popc(ballot & ((1u << lane_id()) - 1u));
+}
+
+__global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdArgs a)
+{
+    __shared__ float s_view[16], s_proj[16];
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_tiles[8];
+
+    if (threadIdx.x < 16) {
+        s_view[threadIdx.x] = a.view[threadIdx.x];
+        s_proj[threadIdx.x] = a.proj[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int idx = blockIdx.x * PRE_BLOCK + threadIdx.x;
+    bool visible = false;
+    bool filtered = false;
+    int radius_out = 0;
+    float4 A, B, C;
+    ushort4 rect = {0, 0, 0, 0};
+    unsigned clamp_bits = 0;
+    uint32_t tiles = 0;
+
+    if (idx < a.P) {
+        const float3 p_orig = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+        // near cull (auxiliary.h:139-164); the +-1.3 NDC test is disabled in the reference
+        const float4 p_hom = xform_point_h(p_orig, s_proj);
+        const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+        const float3 p_view = xform_point(p_orig, s_view);
+        if (p_view.z <= 0.2f) {
+            filtered = a.prefiltered != 0;
+        } else {
+            float cov3D[6];
+            if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) cov3D[i] = a.cov3D_precomp[6 * (size_t)idx + i];
+            } else {
+                const float3 sc = {a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]};
+                const float4 q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+                cov3d_from_scale_rot(sc, a.scale_modifier, q, cov3D);
+            }
+            const float3 cov = cov2d_project(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, s_view, nullptr);
+            const float det = (cov.x * cov.z - cov.y * cov.y);
+            if (det != 0.0f) {
+                const float det_inv = 1.f / det;
+                const float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+                const float mid = 0.5f * (cov.x + cov.z);
+                const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+                const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+                const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+                const float2 point_image = {ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H)};
+                uint2 rmin, rmax;
+                tile_rect(point_image, my_radius, a.grid_x, a.grid_y, rmin, rmax);
+                if ((rmax.x - rmin.x) * (rmax.y - rmin.y) != 0) {
+                    visible = true;
+                    float3 rgb;
+                    if (a.colors_precomp == nullptr) {
+                        const float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
+                        rgb = sh_to_rgb(a.D, p_orig, campos, reinterpret_cast<const float3*>(a.shs) + (size_t)idx * a.M, clamp_bits);
+                    } else {
+                        rgb = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
+                    }
+                    float s0 = 0.f, s1 = 0.f;
+                    if (a.S == 2 && a.segments != nullptr) {
+                        const float2 sg = *reinterpret_cast<const float2*>(a.segments + 2 * (size_t)idx);
+                        s0 = sg.x;
+                        s1 = sg.y;
+                    }
+                    radius_out = my_radius;
+                    A = {point_image.x, point_image.y, conic.x, conic.y};
+                    B = {conic.z, a.opacities[idx], rgb.x, rgb.y};
+                    C = {rgb.z, p_view.z, s0, s1};
+                    rect = {(unsigned short)rmin.x, (unsigned short)rmin.y, (unsigned short)rmax.x, (unsigned short)rmax.y};
+                    tiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
+                }
+            }
+        }
+        a.radii[idx] = radius_out;
+    }
+
+    // slot compaction inside the block (stable in Gaussian-id order)
+    uint32_t nvis;
+    const uint32_t rank = block_rank_256(visible, s_warp, nvis);
+    if (visible) {
+        const uint32_t slot = blockIdx.x * PRE_BLOCK + rank;
+        a.g.rec[3 * (size_t)slot + 0] = A;
+        a.g.rec[3 * (size_t)slot + 1] = B;
+        a.g.rec[3 * (size_t)slot + 2] = C;
+        a.g.rect[slot] = rect;
+        a.g.slot_gid[slot] = (uint32_t)idx;
+        a.g.clamped[slot] = (uint8_t)clamp_bits;
+    }
+    // instance count of the block -> global R (integer atomics: deterministic total)
+    uint32_t t = tiles;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane_id() == 0) s_tiles[threadIdx.x >> 5] = t;
+    const uint32_t any_filtered = __syncthreads_or(filtered ? 1 : 0);
+    if (threadIdx.x == 0) {
+        uint32_t tt = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tt += s_tiles[w];
+        a.g.blk_count[blockIdx.x] = nvis;
+        if (tt) atomicAdd(reinterpret_cast<unsigned long long*>(a.g.counters + CNT_RENDERED_LO), (unsigned long long)tt);
+        if (any_filtered) atomicOr(a.g.counters + CNT_ERROR, 1u);
+    }
+}
+
+// Exclusive scan of the per-block visible counts (nblk <= a few 10^4): one CTA, chunked with a running carry.
+// Writes blk_offset[0..nblk] (last = V) and counters[CNT_VISIBLE] = V.
+__global__ void __launch_bounds__(1024) block_offsets_kernel(GeomState g)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < g.nblk; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < g.nblk ? g.blk_count[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= (uint32_t)o) w += n;
+            }
+            s_warp[lane] = w; // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t warp_base = warp ? s_warp[warp - 1] : 0u;
+        if (i < g.nblk) g.blk_offset[i] = carry + warp_base + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + warp_base + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        g.blk_offset[g.nblk] = s_carry;
+        g.counters[CNT_VISIBLE] = s_carry;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(PRE_BLOCK) preprocess_bwd_kernel(const PreBwdArgs a)
+{
+    __shared__ float s_view[16], s_proj[16];
+    __shared__ uint32_t s_warp[8];
+    if (threadIdx.x < 16) {
+        s_view[threadIdx.x] = a.view[threadIdx.x];
+        s_proj[threadIdx.x] = a.proj[threadIdx.x];
+    }
+    const int idx = blockIdx.x * PRE_BLOCK + threadIdx.x;
+    const bool visible = idx < a.P && a.radii[idx] > 0;
+    uint32_t nvis;
+    const uint32_t rank = block_rank_256(visible, s_warp, nvis); // contains the __syncthreads for s_view/s_proj
+    if (idx >= a.P) return;
+
+    float3 dL_dmean = {0.f, 0.f, 0.f};
+    float2 dL_dmean2D = {0.f, 0.f};
+    float dL_dcov3D[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float3 dL_dscale = {0.f, 0.f, 0.f};
+    float4 dL_drot = {0.f, 0.f, 0.f, 0.f};
+    float3 dL_dcolor = {0.f, 0.f, 0.f};
+    float2 dL_dseg = {0.f, 0.f};
+    float dL_dopacity = 0.f;
+    V3 dsh[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) dsh[k] = {0.f, 0.f, 0.f};
+
+    if (visible) {
+        const uint32_t slot = blockIdx.x * PRE_BLOCK + rank;
+        const float4* gr = reinterpret_cast<const float4*>(a.grad_rec + (size_t)slot * GRAD_REC_FLOATS);
+        const float4 g0 = gr[0]; // dcolor.rgb, ddepth
+        const float4 g1 = gr[1]; // dseg0, dseg1, dmean2D.x, dmean2D.y
+        const float4 g2 = gr[2]; // dconic.x, dconic.y, dconic.w, dopacity
+        dL_dcolor = {g0.x, g0.y, g0.z};
+        const float dL_ddepth = g0.w;
+        dL_dseg = {g1.x, g1.y};
+        dL_dmean2D = {g1.z, g1.w};
+        dL_dopacity = g2.w;
+
+        const float3 mean = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+        float3 sc = {0.f, 0.f, 0.f};
+        float4 q = {0.f, 0.f, 0.f, 0.f};
+        float cov3D[6];
+        if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) cov3D[i] = a.cov3D_precomp[6 * (size_t)idx + i];
+        } else {
+            sc = {a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]};
+            q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+            cov3d_from_scale_rot(sc, a.scale_modifier, q, cov3D); // same bits as the forward's (recomputed, not stored)
+        }
+
+        // ---- conic -> cov2D -> cov3D and the covariance path of the mean (backward.cu:159-273) ----
+        const float3 dL_dconic = {g2.x, g2.y, g2.z};
+        Cov2DCtx cx;
+        const float3 cv = cov2d_project(mean, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, s_view, &cx);
+        const float h_x = a.focal_x, h_y = a.focal_y;
+        const float x_grad_mul = cx.txtz < -cx.limx || cx.txtz > cx.limx ? 0 : 1;
+        const float y_grad_mul = cx.tytz < -cx.limy || cx.tytz > cx.limy ? 0 : 1;
+        const M3& T = cx.T;
+        const M3& Vrk = cx.Vrk;
+        const M3& W = cx.W;
+        const float3 t = cx.t;
+
+        float aa = cv.x;
+        float b = cv.y;
+        float c = cv.z;
+
+        float denom = aa * c - b * b;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - aa * c) * dL_dconic.z);
+            dL_dc = denom2inv * (-aa * aa * dL_dconic.z + 2 * aa * b * dL_dconic.y + (denom - aa * c) * dL_dconic.x);
+            dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + aa * b * dL_dconic.z);
+
+            dL_dcov3D[0] = (T.c[0][0] * T.c[0][0] * dL_da + T.c[0][0] * T.c[1][0] * dL_db + T.c[1][0] * T.c[1][0] * dL_dc);
+            dL_dcov3D[3] = (T.c[0][1] * T.c[0][1] * dL_da + T.c[0][1] * T.c[1][1] * dL_db + T.c[1][1] * T.c[1][1] * dL_dc);
+            dL_dcov3D[5] = (T.c[0][2] * T.c[0][2] * dL_da + T.c[0][2] * T.c[1][2] * dL_db + T.c[1][2] * T.c[1][2] * dL_dc);
+
+            dL_dcov3D[1] = 2 * T.c[0][0] * T.c[0][1] * dL_da + (T.c[0][0] * T.c[1][1] + T.c[0][1] * T.c[1][0]) * dL_db +
+                           2 * T.c[1][0] * T.c[1][1] * dL_dc;
+            dL_dcov3D[2] = 2 * T.c[0][0] * T.c[0][2] * dL_da + (T.c[0][0] * T.c[1][2] + T.c[0][2] * T.c[1][0]) * dL_db +
+                           2 * T.c[1][0] * T.c[1][2] * dL_dc;
+            dL_dcov3D[4] = 2 * T.c[0][2] * T.c[0][1] * dL_da + (T.c[0][1] * T.c[1][2] + T.c[0][2] * T.c[1][1]) * dL_db +
+                           2 * T.c[1][1] * T.c[1][2] * dL_dc;
+        }
+
+        float dL_dT00 = 2 * (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_da +
+                        (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_db;
+        float dL_dT01 = 2 * (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_da +
+                        (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_db;
+        float dL_dT02 = 2 * (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_da +
+                        (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_db;
+        float dL_dT10 = 2 * (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_dc +
+                        (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_db;
+        float dL_dT11 = 2 * (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_dc +
+                        (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_db;
+        float dL_dT12 = 2 * (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_dc +
+                        (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_db;
+
+        float dL_dJ00 = W.c[0][0] * dL_dT00 + W.c[0][1] * dL_dT01 + W.c[0][2] * dL_dT02;
+        float dL_dJ02 = W.c[2][0] * dL_dT00 + W.c[2][1] * dL_dT01 + W.c[2][2] * dL_dT02;
+        float dL_dJ11 = W.c[1][0] * dL_dT10 + W.c[1][1] * dL_dT11 + W.c[1][2] * dL_dT12;
+        float dL_dJ12 = W.c[2][0] * dL_dT10 + W.c[2][1] * dL_dT11 + W.c[2][2] * dL_dT12;
+
+        float tz = 1.f / t.z;
+        float tz2 = tz * tz;
+        float tz3 = tz2 * tz;
+
+        float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+        float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+        float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
+
+        // transpose of the view rotation (auxiliary.h:89-97)
+        dL_dmean = {s_view[0] * dL_dtx + s_view[1] * dL_dty + s_view[2] * dL_dtz,
+                    s_view[4] * dL_dtx + s_view[5] * dL_dty + s_view[6] * dL_dtz,
+                    s_view[8] * dL_dtx + s_view[9] * dL_dty + s_view[10] * dL_dtz};
+
+        // ---- projection path (backward.cu:372-389) ----
+        const float* proj = s_proj;
+        const float* view = s_view;
+        float4 m_hom = xform_point_h(mean, proj);
+        float m_w = 1.0f / (m_hom.w + 0.0000001f);
+        float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+        float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+        float3 d1;
+        d1.x = (proj[0] * m_w - proj[3] * mul1) * dL_dmean2D.x + (proj[1] * m_w - proj[3] * mul2) * dL_dmean2D.y;
+        d1.y = (proj[4] * m_w - proj[7] * mul1) * dL_dmean2D.x + (proj[5] * m_w - proj[7] * mul2) * dL_dmean2D.y;
+        d1.z = (proj[8] * m_w - proj[11] * mul1) * dL_dmean2D.x + (proj[9] * m_w - proj[11] * mul2) * dL_dmean2D.y;
+        dL_dmean.x += d1.x;
+        dL_dmean.y += d1.y;
+        dL_dmean.z += d1.z;
+
+        // ---- depth path (backward.cu:394-403) ----
+        float mul3 = view[2] * mean.x + view[6] * mean.y + view[10] * mean.z + view[14];
+        float3 d2;
+        d2.x = (view[2] - view[3] * mul3) * dL_ddepth;
+        d2.y = (view[6] - view[7] * mul3) * dL_ddepth;
+        d2.z = (view[10] - view[11] * mul3) * dL_ddepth;
+        dL_dmean.x += d2.x;
+        dL_dmean.y += d2.y;
+        dL_dmean.z += d2.z;
+
+        // ---- SH path ----
+        if (a.shs != nullptr) {
+            const float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
+            const unsigned cb = a.g.clamped[slot];
+            const float3 d3 = sh_backward(a.D, mean, campos, reinterpret_cast<const V3*>(a.shs) + (size_t)idx * a.M, cb,
+                                          V3{dL_dcolor.x, dL_dcolor.y, dL_dcolor.z}, dsh);
+            dL_dmean.x += d3.x;
+            dL_dmean.y += d3.y;
+            dL_dmean.z += d3.z;
+        }
+        // ---- scale / rotation path ----
+        if (a.scales != nullptr) cov3d_backward(sc, a.scale_modifier, q, dL_dcov3D, dL_dscale, dL_drot);
+    }
+
+    // ---- dense gradient rows: every row written exactly once, zeros for invisible Gaussians ----
+    const size_t i = (size_t)idx;
+    if (a.out.dL_dmeans3D) {
+        a.out.dL_dmeans3D[3 * i + 0] = dL_dmean.x;
+        a.out.dL_dmeans3D[3 * i + 1] = dL_dmean.y;
+        a.out.dL_dmeans3D[3 * i + 2] = dL_dmean.z;
+    }
+    if (a.out.dL_dmeans2D) {
+        a.out.dL_dmeans2D[3 * i + 0] = dL_dmean2D.x;
+        a.out.dL_dmeans2D[3 * i + 1] = dL_dmean2D.y;
+        a.out.dL_dmeans2D[3 * i + 2] = 0.f;
+    }
+    if (a.out.dL_dopacity) a.out.dL_dopacity[i] = dL_dopacity;
+    if (a.out.dL_dcolors) {
+        a.out.dL_dcolors[3 * i + 0] = dL_dcolor.x;
+        a.out.dL_dcolors[3 * i + 1] = dL_dcolor.y;
+        a.out.dL_dcolors[3 * i + 2] = dL_dcolor.z;
+    }
+    if (a.out.dL_dsegments && a.S == 2) *reinterpret_cast<float2*>(a.out.dL_dsegments + 2 * i) = dL_dseg;
+    if (a.out.dL_dscales) {
+        a.out.dL_dscales[3 * i + 0] = dL_dscale.x;
+        a.out.dL_dscales[3 * i + 1] = dL_dscale.y;
+        a.out.dL_dscales[3 * i + 2] = dL_dscale.z;
+    }
+    if (a.out.dL_drotations) *reinterpret_cast<float4*>(a.out.dL_drotations + 4 * i) = dL_drot;
+    if (a.out.dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.out.dL_dcov3D[6 * i + k] = dL_dcov3D[k];
+    }
+    if (a.out.dL_dsh) {
+        float* row = a.out.dL_dsh + i * (size_t)a.M * 3;
+        if (a.M == 16) {
+            float4* row4 = reinterpret_cast<float4*>(row); // 192-B rows: 16-B aligned
+            const float* f = reinterpret_cast<const float*>(dsh);
+#pragma unroll
+            for (int k = 0; k < 12; k++) row4[k] = {f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]};
+        } else {
+            const float* f = reinterpret_cast<const float*>(dsh);
+            for (int k = 0; k < a.M * 3; k++) row[k] = k < 48 ? f[k] : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                                           uint8_t* __restrict__ present)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    const float z = view[2] * p.x + view[6] * p.y + view[10] * p.z + view[14];
+    present[idx] = z > 0.2f ? 1 : 0;
+}
+} // namespace
+
+int launch_preprocess_fwd(const PreFwdArgs& a, cudaStream_t s)
+{
+    if (a.P <= 0) return 0;
+    preprocess_fwd_kernel<<<a.g.nblk, PRE_BLOCK, 0, s>>>(a);
+    return 0;
+}
+int launch_block_offsets(const GeomState& g, cudaStream_t s)
+{
+    block_offsets_kernel<<<1, 1024, 0, s>>>(g);
+    return 0;
+}
+int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
+{
+    if (a.P <= 0) return 0;
+    preprocess_bwd_kernel<<<a.g.nblk, PRE_BLOCK, 0, s>>>(a);
+    return 0;
+}
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s)
+{
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+    return 0;
+}
+} // namespace gsr

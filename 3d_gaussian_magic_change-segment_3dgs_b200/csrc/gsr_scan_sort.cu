@@ -1,0 +1,225 @@
+// Device-wide primitives written for this pipeline: an exclusive u32 scan and a stable LSD radix sort of
+// (u32 key, u32 value) pairs. They replace cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:281) and
+// cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:307-312; simple_knn.cu:213) of the reference.
+//
+// Sort design: the reference sorts R 64-bit (tile|depth) keys in 6 passes. Here the visible Gaussians (V << R)
+// are depth-sorted once on their 32 depth bits, instances are emitted in that order, and only the tile id
+// (<= 16 bits -> 2 passes) is sorted at instance granularity. Both sorts are stable, so the final order equals
+// the reference's (tile, depth, Gaussian id) order bit for bit.
+#include "gsr_common.cuh"
+
+namespace gsr
+{
+namespace
+{
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = SCAN_ITEMS / SCAN_THREADS; // 8
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v += n;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix, total in `total`
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/, uint32_t& total)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) base += c;
+        tot += c;
+    }
+    total = tot;
+    __syncthreads();
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ partials)
+{
+    __shared__ uint32_t s_warp[8];
+    const uint32_t base = blockIdx.x * SCAN_ITEMS;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        const uint32_t i = base + k * SCAN_THREADS + threadIdx.x;
+        if (i < n) sum += in[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_warp[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
+// Each CTA sums the partials of the CTAs before it (a few hundred values), then scans its own 2048 items.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* in, uint32_t n, const uint32_t* __restrict__ partials,
+                                                                  uint32_t* out, int write_total)
+{
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_prefix;
+    uint32_t pre = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += SCAN_THREADS) pre += partials[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = pre;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_warp[w];
+        s_prefix = t;
+    }
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+
+    // thread t owns items [t*8, t*8+8) of the CTA tile
+    const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    uint32_t total;
+    uint32_t excl = block_excl_scan_256(sum, s_warp, total) + prefix;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        if (base + k < n) out[base + k] = excl;
+        excl += v[k];
+    }
+    // the thread that owns item n-1 also writes out[n] = grand total
+    if (write_total && n > 0 && base <= n - 1 && n - 1 < base + SCAN_PER_THREAD) out[n] = excl;
+}
+
+// ------------------------------------------------------------------------------------------ radix sort
+constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_PER_THREAD = RADIX_ITEMS / RADIX_THREADS; // 16
+constexpr int RADIX_WARP_ITEMS = RADIX_ITEMS / 8;             // 512 consecutive keys per warp
+
+// Per-CTA digit histogram, written digit-major: hist[d * nblocks + block].
+__global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t mask,
+                                                                   uint32_t nblocks, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RADIX_ITEMS;
+#pragma unroll
+    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+        const uint32_t i = base + k * RADIX_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x <= mask) hist[threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+// Stable scatter. Warp w of the CTA owns keys [w*512, w*512+512) of the CTA tile and walks them in order, 32 at a
+// time; ranks inside a 32-key step come from match.any, ranks across steps / warps / CTAs from counters.
+__global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                                                                      int shift, uint32_t mask, uint32_t nblocks,
+                                                                      const uint32_t* __restrict__ offsets /* scanned hist */)
+{
+    __shared__ uint32_t s_cnt[8][256];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 8 * 256; i += RADIX_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const uint32_t wbase = blockIdx.x * RADIX_ITEMS + warp * RADIX_WARP_ITEMS;
+    uint32_t key[RADIX_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+        const uint32_t i = wbase + k * 32 + lane;
+        key[k] = i < n ? keys_in[i] : 0xffffffffu;
+        if (i < n) atomicAdd(&s_cnt[warp][(key[k] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    // turn per-warp counts into global base positions: offsets[d][block] + counts of earlier warps
+    if (threadIdx.x <= mask) {
+        uint32_t run = offsets[threadIdx.x * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint32_t c = s_cnt[w][threadIdx.x];
+            s_cnt[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+        const uint32_t i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        // invalid lanes get a digit outside the histogram so they never match a valid lane
+        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0x100u + lane;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t pos = 0;
+        if (valid) pos = s_cnt[warp][d] + rank;
+        __syncwarp();
+        if (valid && rank == 0) s_cnt[warp][d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            keys_out[pos] = key[k];
+            vals_out[pos] = vals_in[i];
+        }
+    }
+}
+} // namespace
+
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, bool write_total, uint32_t* partials, cudaStream_t s)
+{
+    if (n == 0) {
+        if (write_total) GSR_CUDA(cudaMemsetAsync(out, 0, sizeof(uint32_t), s));
+        return 0;
+    }
+    const uint32_t nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, partials);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, partials, out, write_total ? 1 : 0);
+    return 0;
+}
+
+int radix_num_passes(int nbits) { return nbits <= 0 ? 0 : (nbits + 7) / 8; }
+
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* hist, size_t hist_words, cudaStream_t s)
+{
+    const int passes = radix_num_passes(nbits);
+    if (n == 0 || passes == 0) return 0;
+    const uint32_t nb = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    const int digit_bits = (nbits + passes - 1) / passes;
+    const uint32_t bins = 1u << digit_bits;
+    const size_t hwords = (size_t)bins * nb;
+    const size_t pwords = (hwords + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    if (hwords + pwords > hist_words) {
+        set_error("radix_sort_pairs: histogram workspace too small (%zu > %zu words)", hwords + pwords, hist_words);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    uint32_t* partials = hist + hwords;
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+        const int shift = p * digit_bits;
+        const uint32_t mask = bins - 1;
+        radix_hist_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], n, shift, mask, nb, hist);
+        int rc = exclusive_scan_u32(hist, hist, (uint32_t)hwords, false, partials, s);
+        if (rc) return rc;
+        radix_scatter_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, mask, nb, hist);
+        cur ^= 1;
+    }
+    return cur;
+}
+} // namespace gsr

@@ -1,0 +1,350 @@
+"""Drop-in `diff_gaussian_rasterization` over libgsr (B200 / sm_100a).
+
+Mirrors the public surface of the reference module
+(submodules_local/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py:21-235):
+
+    GaussianRasterizationSettings   NamedTuple, same field order            (:168-180)
+    GaussianRasterizer              nn.Module: markVisible(), forward()     (:182-235)
+    rasterize_gaussians(...)        -> (color, radii, depth, alpha, segment) (:21-44, :102)
+
+so `gaussian_renderer.render()`, `train.py` and `train_segment.py` run unchanged with this directory's parent on
+`sys.path`. The native side is the C-ABI library libgsr.so (include/gsr.h), called through ctypes with raw
+device pointers on `torch.cuda.current_stream()`; torch only owns memory and streams. There is no CPU path:
+CPU tensors raise.
+"""
+import ctypes
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+
+
+def _load_lib_module():
+    """Load ../_lib.py (the ctypes binding of libgsr.so) by path, once, whichever way this module was imported:
+    as a sub-package of the b200 package or as top-level `diff_gaussian_rasterization` from a sys.path entry."""
+    import importlib.util
+    import os
+    import sys
+
+    name = "_gsr_b200_lib"
+    if name in sys.modules:
+        return sys.modules[name]
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_lib.py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_lib = _load_lib_module()
+ALLOC_FN, GsrGaussians, GsrOutputs, GsrParamGrads = _lib.ALLOC_FN, _lib.GsrGaussians, _lib.GsrOutputs, _lib.GsrParamGrads
+GsrPixelGrads, GsrState, GsrStateExport, GsrView = _lib.GsrPixelGrads, _lib.GsrState, _lib.GsrStateExport, _lib.GsrView
+
+NUM_CHANNELS = 3  # cuda_rasterizer/config.h:15
+NUM_CLASS = 2     # cuda_rasterizer/config.h:16 (segment channels rendered when `segments` is absent)
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+def _ptr(t):
+    """Device pointer of a tensor; empty tensors are the reference's "not provided" sentinel (-> NULL)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _prep(t, device, what):
+    """contiguous fp32 on the compute device (the reference calls .contiguous().data<float>())."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.device != device:
+        raise RuntimeError("%s must be on %s (got %s); libgsr has no CPU path" % (what, device, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32 (got %s)" % (what, t.dtype))
+    return t.contiguous()
+
+
+class _Alloc:
+    """gsr_alloc_fn: hands libgsr torch-owned byte buffers (the reference's resizeFunctional, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = [None, None, None]
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, user, which, nbytes):
+        try:
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+            self.bufs[which] = t
+            return t.data_ptr()
+        except Exception:  # report as allocation failure through the C ABI
+            return 0
+
+
+def _view_struct(rs, M, num_class, keep):
+    bg = _prep(rs.bg, keep["device"], "bg")
+    vm = _prep(rs.viewmatrix, keep["device"], "viewmatrix")
+    pm = _prep(rs.projmatrix, keep["device"], "projmatrix")
+    cp = _prep(rs.campos, keep["device"], "campos")
+    keep["view_tensors"] = (bg, vm, pm, cp)
+    return GsrView(int(rs.image_width), int(rs.image_height), float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
+                   int(rs.sh_degree), int(M), int(num_class), int(bool(rs.prefiltered)), int(bool(rs.debug)),
+                   _ptr(bg), _ptr(vm), _ptr(pm), _ptr(cp))
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp,
+                                     raster_settings)
+
+
+def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, rs):
+    """RasterizeGaussiansCUDA (rasterize_points.cu:35-125) over gsr_forward. Returns the reference's 9-tuple
+    (num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer)."""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor; libgsr has no CPU path")
+    L = _lib.lib()
+    device = means3D.device
+    P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
+    num_class = segments.size(1) if (segments is not None and segments.numel() > 0) else NUM_CLASS
+    with torch.cuda.device(device):
+        opts = dict(dtype=torch.float32, device=device)
+        if P == 0:  # the core is skipped; images stay zero (background NOT applied), rasterize_points.cu:87
+            z = lambda c: torch.zeros((c, H, W), **opts)
+            e = lambda: torch.empty(0, dtype=torch.uint8, device=device)
+            return 0, z(NUM_CHANNELS), z(1), z(num_class), z(1), torch.zeros(0, dtype=torch.int32, device=device), e(), e(), e()
+        keep = {"device": device}
+        M = sh.size(1) if (sh is not None and sh.numel() > 0) else 0
+        view = _view_struct(rs, M, num_class, keep)
+        t_means = _prep(means3D, device, "means3D")
+        t_sh, t_col = _prep(sh, device, "sh"), _prep(colors_precomp, device, "colors_precomp")
+        t_seg, t_op = _prep(segments, device, "segments"), _prep(opacities, device, "opacities")
+        t_sc, t_rot = _prep(scales, device, "scales"), _prep(rotations, device, "rotations")
+        t_cov = _prep(cov3Ds_precomp, device, "cov3Ds_precomp")
+        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), _ptr(t_op), _ptr(t_sc), _ptr(t_rot), _ptr(t_cov))
+        color = torch.empty((NUM_CHANNELS, H, W), **opts)
+        segment = torch.empty((num_class, H, W), **opts)
+        depth = torch.empty((1, H, W), **opts)
+        alpha = torch.empty((1, H, W), **opts)
+        radii = torch.empty(P, dtype=torch.int32, device=device)
+        out = GsrOutputs(color.data_ptr(), segment.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii.data_ptr())
+        alloc = _Alloc(device)
+        R = ctypes.c_int32(0)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = L.gsr_forward(ctypes.byref(view), ctypes.byref(gin), ctypes.byref(out), alloc.cb, None, ctypes.byref(R), stream)
+        _lib.check(rc, "gsr_forward")
+        e = lambda t: t if t is not None else torch.empty(0, dtype=torch.uint8, device=device)
+        return R.value, color, depth, segment, alpha, radii, e(alloc.bufs[0]), e(alloc.bufs[1]), e(alloc.bufs[2])
+
+
+def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotations, cov3Ds_precomp, grad_color, grad_segment, grad_depth,
+                     grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, needs=None):
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:127-221) over gsr_backward. Returns a dict of dense
+    gradients (zeros for invisible Gaussians). `needs` optionally names the gradients to produce."""
+    L = _lib.lib()
+    device = means3D.device
+    P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
+    M = sh.size(1) if (sh is not None and sh.numel() > 0) else 0
+    num_class = segments.size(1) if (segments is not None and segments.numel() > 0) else NUM_CLASS
+    names = ["means3D", "means2D", "sh", "colors_precomp", "segments", "opacities", "scales", "rotations", "cov3Ds_precomp"]
+    want = {n: True for n in names} if needs is None else {n: bool(needs.get(n, False)) for n in names}
+    have = {"sh": M > 0, "colors_precomp": colors_precomp is not None and colors_precomp.numel() > 0,
+            "segments": segments is not None and segments.numel() > 0,
+            "scales": scales is not None and scales.numel() > 0, "rotations": rotations is not None and rotations.numel() > 0,
+            "cov3Ds_precomp": cov3Ds_precomp is not None and cov3Ds_precomp.numel() > 0}
+    shapes = {"means3D": (P, 3), "means2D": (P, 3), "sh": (P, M, 3), "colors_precomp": (P, 3), "segments": (P, num_class),
+              "opacities": (P, 1), "scales": (P, 3), "rotations": (P, 4), "cov3Ds_precomp": (P, 6)}
+    with torch.cuda.device(device):
+        opts = dict(dtype=torch.float32, device=device)
+        grads = {}
+        for n in names:
+            if want[n] and have.get(n, True):
+                grads[n] = torch.zeros(shapes[n], **opts) if P == 0 else torch.empty(shapes[n], **opts)
+            else:
+                grads[n] = None
+        if P == 0:
+            return grads
+        keep = {"device": device}
+        view = _view_struct(rs, M, num_class, keep)
+        t_means = _prep(means3D, device, "means3D")
+        t_sh, t_col = _prep(sh, device, "sh"), _prep(colors_precomp, device, "colors_precomp")
+        t_seg = _prep(segments, device, "segments")
+        t_sc, t_rot = _prep(scales, device, "scales"), _prep(rotations, device, "rotations")
+        t_cov = _prep(cov3Ds_precomp, device, "cov3Ds_precomp")
+        # opacities are not needed: they live in the saved geometry state (as in the reference, conic_opacity.w)
+        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), t_means.data_ptr(), _ptr(t_sc), _ptr(t_rot), _ptr(t_cov))
+        g_col = _prep(grad_color, device, "grad_color")
+        if g_col is None:
+            g_col = torch.zeros((NUM_CHANNELS, H, W), **opts)
+        g_seg, g_dep, g_alp = _prep(grad_segment, device, "grad_segment"), _prep(grad_depth, device, "grad_depth"), _prep(grad_alpha, device, "grad_alpha")
+        pix = GsrPixelGrads(g_col.data_ptr(), _ptr(g_seg), _ptr(g_dep), _ptr(g_alp))
+        pg = GsrParamGrads(_ptr(grads["means3D"]), _ptr(grads["means2D"]), _ptr(grads["sh"]), _ptr(grads["colors_precomp"]),
+                           _ptr(grads["segments"]), _ptr(grads["opacities"]), _ptr(grads["scales"]), _ptr(grads["rotations"]),
+                           _ptr(grads["cov3Ds_precomp"]))
+        state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
+        nscratch = L.gsr_backward_scratch_bytes(P)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
+        t_radii = radii.contiguous()
+        t_alpha = _prep(alpha, device, "alpha")
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = L.gsr_backward(ctypes.byref(view), ctypes.byref(gin), t_radii.data_ptr(), ctypes.byref(state), t_alpha.data_ptr(),
+                            ctypes.byref(pix), ctypes.byref(pg), scratch.data_ptr(), nscratch, stream)
+        _lib.check(rc, "gsr_backward")
+        return grads
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        args = (means3D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args[:-1] + tuple(raster_settings))  # copy before they can be corrupted
+            try:
+                num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer = _forward_native(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer = _forward_native(*args)
+
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None -> NULL (= zeros) instead of zero-filled tensors
+        ctx.mark_non_differentiable(radii)
+        ctx.save_for_backward(colors_precomp, segments, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
+                              imgBuffer, alpha)
+        return color, radii, depth, alpha, segment
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha, grad_segment):
+        num_rendered = ctx.num_rendered
+        rs = ctx.raster_settings
+        colors_precomp, segments, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer, alpha = ctx.saved_tensors
+        nig = ctx.needs_input_grad
+        needs = {"means3D": nig[0], "means2D": nig[1], "sh": nig[2], "colors_precomp": nig[3], "segments": nig[4], "opacities": nig[5],
+                 "scales": nig[6], "rotations": nig[7], "cov3Ds_precomp": nig[8]}
+        args = (rs, means3D, radii, colors_precomp, segments, scales, rotations, cov3Ds_precomp, grad_color, grad_segment, grad_depth,
+                grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha)
+        if rs.debug:
+            cpu_args = cpu_deep_copy_tuple(tuple(rs) + args[1:])
+            try:
+                g = _backward_native(*args, needs=needs)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            g = _backward_native(*args, needs=needs)
+        return (g["means3D"], g["means2D"], g["sh"], g["colors_precomp"], g["segments"], g["opacities"], g["scales"], g["rotations"],
+                g["cov3Ds_precomp"], None)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def mark_visible(positions, viewmatrix, projmatrix):
+    """_C.mark_visible (rasterize_points.cu:223-242): bool[P], true where view-space z > 0.2."""
+    L = _lib.lib()
+    if not positions.is_cuda:
+        raise RuntimeError("positions must be a CUDA tensor; libgsr has no CPU path")
+    device = positions.device
+    P = positions.size(0)
+    with torch.cuda.device(device):
+        present = torch.zeros(P, dtype=torch.bool, device=device)
+        if P:
+            pos = _prep(positions, device, "positions")
+            vm, pm = _prep(viewmatrix, device, "viewmatrix"), _prep(projmatrix, device, "projmatrix")
+            rc = L.gsr_mark_visible(P, pos.data_ptr(), vm.data_ptr(), pm.data_ptr(), present.data_ptr(),
+                                    torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(rc, "gsr_mark_visible")
+        return present
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            rs = self.raster_settings
+            visible = mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+        return visible
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, segments=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        # absent optionals travel as empty tensors, the reference's "not provided" sentinel (__init__.py:208-221)
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if segments is None:
+            segments = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, segments, opacities, scales, rotations, cov3D_precomp,
+                                   raster_settings)
+
+
+def export_state(P, W, H, geomBuffer, binningBuffer, imgBuffer, num_rendered):
+    """Test support: unpack the opaque forward state into the reference's Gaussian-id-indexed arrays
+    (gsr_export_state). Returns a dict of tensors."""
+    L = _lib.lib()
+    device = geomBuffer.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    R = int(num_rendered)
+    with torch.cuda.device(device):
+        o = {
+            "depths": torch.empty(P, dtype=torch.float32, device=device),
+            "means2D": torch.empty((P, 2), dtype=torch.float32, device=device),
+            "conic_opacity": torch.empty((P, 4), dtype=torch.float32, device=device),
+            "rgb": torch.empty((P, 3), dtype=torch.float32, device=device),
+            "clamped": torch.empty((P, 3), dtype=torch.uint8, device=device),
+            "tiles_touched": torch.empty(P, dtype=torch.int32, device=device),
+            "point_keys": torch.zeros(max(R, 1), dtype=torch.int64, device=device),
+            "point_list": torch.zeros(max(R, 1), dtype=torch.int32, device=device),
+            "ranges": torch.empty((T, 2), dtype=torch.int32, device=device),
+            "n_contrib": torch.empty(H * W, dtype=torch.int32, device=device),
+        }
+        ex = GsrStateExport(*[o[k].data_ptr() for k in ["depths", "means2D", "conic_opacity", "rgb", "clamped", "tiles_touched", "point_keys",
+                                                       "point_list", "ranges", "n_contrib"]])
+        st = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), R)
+        rc = L.gsr_export_state(P, W, H, ctypes.byref(st), ctypes.byref(ex), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "gsr_export_state")
+        o["point_keys"] = o["point_keys"][:R]
+        o["point_list"] = o["point_list"][:R]
+        return o

@@ -1,0 +1,165 @@
+/*
+ * libgsr -- B200-native (sm_100a) differentiable Gaussian-splatting rasterizer + simple-knn.
+ *
+ * C ABI of the drop-in boundary. Every entry point replaces one native entry point of the reference
+ * (paths relative to /root/reference/submodules_local/):
+ *
+ *   gsr_forward        <- RasterizeGaussiansCUDA            diff-gaussian-rasterization/rasterize_points.cu:35-125
+ *                         CudaRasterizer::Rasterizer::forward   cuda_rasterizer/rasterizer_impl.cu:198-344
+ *   gsr_backward       <- RasterizeGaussiansBackwardCUDA    rasterize_points.cu:127-221
+ *                         Rasterizer::backward                  cuda_rasterizer/rasterizer_impl.cu:348-458
+ *   gsr_mark_visible   <- markVisible                       rasterize_points.cu:223-242 (rasterizer_impl.cu:141-153)
+ *   gsr_knn_dist2      <- distCUDA2 / SimpleKNN::knn        simple-knn/spatial.cu:15-26, simple_knn.cu:185-221
+ *   gsr_alloc_fn       <- std::function<char*(size_t)> resizeFunctional   rasterize_points.cu:27-33
+ *
+ * Plain pointers and sizes only: no torch types. All data pointers are DEVICE pointers on the device that is
+ * current on the calling thread; the structs themselves live in host memory. All work is enqueued on `stream`
+ * (a cudaStream_t). gsr_forward synchronises `stream` once (to learn the number of tile instances, like the
+ * reference's blocking 4-byte read at rasterizer_impl.cu:285); nothing else blocks unless view->debug != 0.
+ * Functions return 0 on success or a negative GSR_ERR_* code; gsr_last_error() describes the last failure on
+ * the calling thread. There is no CPU fallback anywhere in this library.
+ */
+#ifndef GSR_H_INCLUDED
+#define GSR_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+#define GSR_OK 0
+#define GSR_ERR_INVALID_ARGUMENT (-1)
+#define GSR_ERR_CUDA (-2)
+#define GSR_ERR_ALLOC (-3)
+#define GSR_ERR_PREFILTERED (-4) /* prefiltered=1 but a Gaussian was culled (reference: printf + __trap) */
+#define GSR_ERR_UNSUPPORTED (-5)
+#define GSR_ERR_OVERFLOW (-6) /* more than 2^31-1 tile instances */
+
+typedef void* gsr_stream_t; /* cudaStream_t */
+
+/* State buffers, same three as the reference (geomBuffer, binningBuffer, imgBuffer). Contents are opaque and
+ * differ from the reference's layout; they must be handed back unchanged to gsr_backward. */
+enum { GSR_BUF_GEOM = 0, GSR_BUF_BINNING = 1, GSR_BUF_IMG = 2 };
+
+/* Called by gsr_forward to obtain each state buffer once its size is known. Must return a device pointer
+ * aligned to >= 256 bytes (NULL = failure). bytes may be 0. */
+typedef void* (*gsr_alloc_fn)(void* user, int which, size_t bytes);
+
+/* Per-view constants: GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:168-180). */
+typedef struct GsrView {
+    int32_t image_width, image_height;
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    int32_t sh_degree;   /* D: active degree 0..3 */
+    int32_t sh_coeffs;   /* M: coefficients per Gaussian in `shs` (0 when shs == NULL) */
+    int32_t num_class;   /* channels of `segments` / out segment (reference NUM_CLASS = 2, config.h:16); 0 or 2 */
+    int32_t prefiltered;
+    int32_t debug;       /* != 0: synchronise and check after every stage (auxiliary.h:166-173) */
+    const float* bg;         /* [3] */
+    const float* viewmatrix; /* [16], as the reference receives it (world_view_transform, column-major for the kernels) */
+    const float* projmatrix; /* [16] full_proj_transform */
+    const float* campos;     /* [3] */
+} GsrView;
+
+/* Gaussian inputs, row-major contiguous fp32. NULL = "not provided" (the reference's empty-tensor sentinel). */
+typedef struct GsrGaussians {
+    int32_t P;
+    const float* means3D;        /* [P,3] */
+    const float* shs;            /* [P,M,3] or NULL */
+    const float* colors_precomp; /* [P,3] or NULL */
+    const float* segments;       /* [P,num_class] or NULL (then the segment output is zero) */
+    const float* opacities;      /* [P] */
+    const float* scales;         /* [P,3] or NULL */
+    const float* rotations;      /* [P,4] (w,x,y,z; used un-normalised) or NULL */
+    const float* cov3D_precomp;  /* [P,6] or NULL */
+} GsrGaussians;
+
+/* Forward outputs; every element is written by the kernels (no pre-zeroing needed) when P > 0. */
+typedef struct GsrOutputs {
+    float* color;   /* [3,H,W] */
+    float* segment; /* [num_class,H,W] (may be NULL when num_class == 0) */
+    float* depth;   /* [1,H,W] */
+    float* alpha;   /* [1,H,W] = sum_i alpha_i T_i */
+    int32_t* radii; /* [P] */
+} GsrOutputs;
+
+typedef struct GsrState {
+    void* geom;
+    void* binning;
+    void* img;
+    int32_t num_rendered; /* R, as returned by gsr_forward */
+} GsrState;
+
+typedef struct GsrPixelGrads {
+    const float* dL_dcolor;   /* [3,H,W] */
+    const float* dL_dsegment; /* [num_class,H,W] or NULL (= zeros) */
+    const float* dL_ddepth;   /* [1,H,W] or NULL (= zeros) */
+    const float* dL_dalpha;   /* [1,H,W] or NULL (= zeros) */
+} GsrPixelGrads;
+
+/* Dense gradients, every row written (zeros for invisible Gaussians). NULL members are skipped. */
+typedef struct GsrParamGrads {
+    float* dL_dmeans3D;   /* [P,3] */
+    float* dL_dmeans2D;   /* [P,3] (third column 0) */
+    float* dL_dsh;        /* [P,M,3] (needs shs) */
+    float* dL_dcolors;    /* [P,3]  gradient w.r.t. colors_precomp (or the internal SH colour) */
+    float* dL_dsegments;  /* [P,num_class] */
+    float* dL_dopacity;   /* [P] */
+    float* dL_dscales;    /* [P,3] (needs scales) */
+    float* dL_drotations; /* [P,4] (needs rotations) */
+    float* dL_dcov3D;     /* [P,6] */
+} GsrParamGrads;
+
+int gsr_abi_version(void);
+const char* gsr_last_error(void);
+
+/* Returns R (>= 0) in *num_rendered. `out->radii` etc. must be valid for P > 0. P == 0 is a no-op returning R = 0
+ * (the host side returns zero images, as rasterize_points.cu:87 does). */
+int gsr_forward(const GsrView* view, const GsrGaussians* in, const GsrOutputs* out, gsr_alloc_fn alloc, void* alloc_user,
+                int32_t* num_rendered, gsr_stream_t stream);
+
+/* Bytes of scratch gsr_backward needs (per-Gaussian gradient records accumulated by the compositing backward). */
+size_t gsr_backward_scratch_bytes(int32_t P);
+
+int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
+                 const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, gsr_stream_t stream);
+
+int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     gsr_stream_t stream);
+
+size_t gsr_knn_workspace_bytes(int32_t P);
+int gsr_knn_dist2(int32_t P, const float* points, float* mean_dist2, void* workspace, size_t workspace_bytes, gsr_stream_t stream);
+
+/* Test/diagnostic support: unpack the opaque state of a forward pass into reference-style, Gaussian-id-indexed
+ * arrays so it can be compared bit for bit with the reference's GeometryState/BinningState/ImageState
+ * (rasterizer_impl.cu:155-194). Every member may be NULL. */
+typedef struct GsrStateExport {
+    float* depths;           /* [P]   geomState.depths (0 for invisible) */
+    float* means2D;          /* [P,2] */
+    float* conic_opacity;    /* [P,4] */
+    float* rgb;              /* [P,3] */
+    uint8_t* clamped;        /* [P,3] */
+    uint32_t* tiles_touched; /* [P] */
+    uint64_t* point_keys;    /* [R] sorted keys  (tile << 32) | depth bits */
+    uint32_t* point_list;    /* [R] sorted Gaussian ids */
+    uint32_t* ranges;        /* [T,2] */
+    uint32_t* n_contrib;     /* [H*W] */
+} GsrStateExport;
+
+int gsr_export_state(int32_t P, int32_t image_width, int32_t image_height, const GsrState* state, const GsrStateExport* out,
+                     gsr_stream_t stream);
+
+/* Per-stage device timings (ms) of the most recent gsr_forward / gsr_backward on this thread when
+ * gsr_set_profiling(1) is active (adds cudaEvent records; used by bench.py for the roofline block). */
+#define GSR_STAGE_COUNT 16
+void gsr_set_profiling(int enable);
+int gsr_get_stage_times(float* ms /*[GSR_STAGE_COUNT]*/, const char** names /*[GSR_STAGE_COUNT]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,133 @@
+"""GPU tests of the drop-in Python surface (GaussianRasterizationSettings / GaussianRasterizer / rasterize_gaussians /
+markVisible) and of the edge cases of SURVEY.md Appendix D that do not need the reference build."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(P, W, Hh, seed):
+    syn = H.synthetic()
+    gs, cam = syn.make_scene(P, W, Hh, seed=seed)
+    return H.to_dev(gs), cam
+
+
+def test_module_forward_backward_autograd():
+    Pk = H.pkg()
+    gs, cam = _mk(20_000, 256, 192, 3)
+    rs = H.settings(cam, torch.zeros(3))
+    leaves = {k: gs[k].clone().requires_grad_(True) for k in ["means3D", "shs", "segments", "opacities", "scales", "rotations"]}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    rast = Pk.GaussianRasterizer(rs)
+    color, radii, depth, alpha, segment = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
+                                               segments=leaves["segments"], scales=leaves["scales"], rotations=leaves["rotations"])
+    assert color.shape == (3, 192, 256) and depth.shape == (1, 192, 256) and alpha.shape == (1, 192, 256)
+    assert segment.shape == (2, 192, 256) and radii.shape == (20_000,) and radii.dtype == torch.int32
+    loss = color.mean() + 0.1 * (depth / (depth.max() + 1e-5)).mean() + 0.05 * segment.mean()
+    loss.backward()
+    for k, v in leaves.items():
+        assert v.grad is not None and v.grad.shape == v.shape and torch.isfinite(v.grad).all(), k
+    assert means2D.grad is not None and float(means2D.grad[:, 2].abs().max()) == 0.0
+    vis = radii > 0
+    assert float(leaves["means3D"].grad[~vis].abs().max()) == 0.0  # dense grads, zero rows for invisible Gaussians
+    assert float(leaves["shs"].grad[~vis].abs().max()) == 0.0
+    assert float(leaves["opacities"].grad[vis].abs().max()) > 0.0
+
+
+def test_validation_messages():
+    Pk = H.pkg()
+    gs, cam = _mk(100, 64, 64, 1)
+    rast = Pk.GaussianRasterizer(H.settings(cam, torch.zeros(3)))
+    m2 = torch.zeros_like(gs["means3D"])
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(means3D=gs["means3D"], means2D=m2, opacities=gs["opacities"], scales=gs["scales"], rotations=gs["rotations"])
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        rast(means3D=gs["means3D"], means2D=m2, opacities=gs["opacities"], shs=gs["shs"], scales=gs["scales"])
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        rast(means3D=gs["means3D"].reshape(-1), means2D=m2, opacities=gs["opacities"], shs=gs["shs"], scales=gs["scales"],
+             rotations=gs["rotations"])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rast(means3D=gs["means3D"].cpu(), means2D=m2, opacities=gs["opacities"], shs=gs["shs"], scales=gs["scales"],
+             rotations=gs["rotations"])
+
+
+def test_empty_input_returns_zero_images():
+    Pk = H.pkg()
+    _, cam = _mk(10, 64, 48, 1)
+    rs = H.settings(cam, torch.ones(3))
+    e = lambda *s: torch.zeros(*s, device="cuda")
+    rast = Pk.GaussianRasterizer(rs)
+    color, radii, depth, alpha, segment = rast(means3D=e(0, 3), means2D=e(0, 3), opacities=e(0, 1), shs=e(0, 16, 3), segments=e(0, 2),
+                                               scales=e(0, 3), rotations=e(0, 4))
+    assert float(color.abs().max()) == 0.0 and radii.numel() == 0  # background NOT applied when P == 0 (rasterize_points.cu:87)
+
+
+def test_nothing_visible_gives_background():
+    gs, cam = _mk(1000, 96, 64, 2)
+    gs["means3D"][:, 2] = -50.0  # all behind the camera
+    rs = H.settings(cam, torch.tensor([0.3, 0.6, 0.9]))
+    ug = H.to_dev(H.synthetic().upstream_grads(96, 64, 2))
+    out = H.run_ours(gs, rs, ug)
+    assert out["num_rendered"] == 0 and int(out["radii"].abs().sum()) == 0
+    assert torch.allclose(out["color"][:, 0, 0], torch.tensor([0.3, 0.6, 0.9], device="cuda"))
+    assert float(out["depth"].abs().max()) == 0 and float(out["alpha"].abs().max()) == 0 and float(out["segment"].abs().max()) == 0
+    assert int(out["state"]["n_contrib"].sum()) == 0
+    for k, v in out["grads"].items():
+        if v is not None:
+            assert float(v.abs().max()) == 0.0, k
+
+
+def test_segments_none_renders_zero_segment():
+    Pk = H.pkg()
+    gs, cam = _mk(5000, 128, 96, 4)
+    rast = Pk.GaussianRasterizer(H.settings(cam, torch.zeros(3)))
+    color, radii, depth, alpha, segment = rast(means3D=gs["means3D"], means2D=torch.zeros_like(gs["means3D"]), opacities=gs["opacities"],
+                                               shs=gs["shs"], scales=gs["scales"], rotations=gs["rotations"])
+    assert segment.shape == (2, 96, 128) and float(segment.abs().max()) == 0.0 and float(color.abs().max()) > 0
+
+
+def test_mark_visible_matches_view_depth():
+    Pk = H.pkg()
+    gs, cam = _mk(50_000, 64, 64, 6)
+    rast = Pk.GaussianRasterizer(H.settings(cam, torch.zeros(3)))
+    vis = rast.markVisible(gs["means3D"])
+    O = H.cpu_oracle()
+    exp = O.mark_visible(gs["means3D"].cpu().numpy(), cam["viewmatrix"].numpy(), cam["projmatrix"].numpy())
+    got = vis.cpu().numpy()
+    assert got.dtype == np.bool_ and (got != exp).mean() <= 1e-4  # fp32 FMA vs non-FMA at the z == 0.2 boundary
+
+
+def test_prefiltered_culled_point_raises():
+    gs, cam = _mk(1000, 64, 64, 8)
+    rs = H.settings(cam, torch.zeros(3), prefiltered=True)
+    with pytest.raises(RuntimeError, match="prefiltered"):
+        H.run_ours(gs, rs)
+
+
+def test_debug_mode_runs():
+    gs, cam = _mk(2000, 96, 64, 9)
+    rs = H.settings(cam, torch.zeros(3), debug=True)
+    out = H.run_ours(gs, rs, H.to_dev(H.synthetic().upstream_grads(96, 64, 9)))
+    assert torch.isfinite(out["color"]).all()
+
+
+def test_tile_lists_are_sorted_partition_full_size():
+    """Size-independent properties at a BASELINE-size case (cfg2 shape, 3M Gaussians, 1297x840): ranges partition
+    [0,R), keys are non-decreasing, sum(tiles_touched) == R, every listed Gaussian is visible."""
+    gs, cam = _mk(3_000_000, 1297, 840, 1)
+    rs = H.settings(cam, torch.zeros(3))
+    out = H.run_ours(gs, rs)
+    st, R = out["state"], out["num_rendered"]
+    assert int(st["tiles_touched"].long().sum()) == R and R > 0
+    keys = st["point_keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())
+    rng = st["ranges"].long()
+    ne = rng[(rng[:, 1] - rng[:, 0]) > 0]
+    assert int((ne[:, 1] - ne[:, 0]).sum()) == R
+    assert bool((ne[1:, 0] == ne[:-1, 1]).all()) and int(ne[0, 0]) == 0 and int(ne[-1, 1]) == R
+    assert bool((out["radii"][st["point_list"].long()] > 0).all())
+    assert bool((st["n_contrib"].view(840, 1297).long() <= (rng[:, 1] - rng[:, 0]).max()).all())
+    assert torch.isfinite(out["color"]).all() and float(out["alpha"].max()) <= 1.0 + 1e-4

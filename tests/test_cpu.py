@@ -1,0 +1,154 @@
+"""CPU-only tests (run with -m "not gpu"): the oracle against golden vectors, host logic, and the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+ROOT = H.ROOT
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_libgsr_loads_and_exports_every_declared_symbol():
+    Pk = H.pkg()
+    lib = Pk._lib.lib()
+    header = open(os.path.join(ROOT, "include", "gsr.h")).read()
+    declared = set(re.findall(r"\b(gsr_[a-z0-9_]+)\s*\(", header)) - {"gsr_alloc_fn"}
+    assert declared, "no declarations parsed"
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), "libgsr.so does not export %s" % sym
+    assert set(Pk._lib.SYMBOLS) == declared
+    assert lib.gsr_abi_version() == 1
+    assert lib.gsr_backward_scratch_bytes(1000) >= 1024 * 48 and lib.gsr_backward_scratch_bytes(0) == 0
+
+
+def test_product_has_no_cpu_fallback():
+    Pk = H.pkg()
+    syn = H.synthetic()
+    gs, cam = syn.make_scene(50, 32, 32, seed=0)
+    rs = Pk.GaussianRasterizationSettings(32, 32, cam["tanfovx"], cam["tanfovy"], torch.zeros(3), 1.0, cam["viewmatrix"], cam["projmatrix"], 3,
+                                          cam["campos"], False, False)
+    rast = Pk.GaussianRasterizer(rs)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rast(means3D=gs["means3D"], means2D=torch.zeros(50, 3), opacities=gs["opacities"], shs=gs["shs"], scales=gs["scales"],
+             rotations=gs["rotations"])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Pk.distCUDA2(torch.rand(10, 3))
+
+
+def test_product_sources_do_not_touch_the_oracle():
+    pk_dir = os.path.join(ROOT, H.PKG_NAME)
+    for dp, _, files in os.walk(pk_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "cpu_oracle" not in txt and "gsr_oracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)
+
+
+def test_synthetic_scene_is_deterministic_and_shaped():
+    syn = H.synthetic()
+    a, cam = syn.make_scene(1000, 800, 800, seed=0)
+    b, _ = syn.make_scene(1000, 800, 800, seed=0)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    assert a["shs"].shape == (1000, 16, 3) and a["opacities"].shape == (1000, 1) and a["segments"].shape == (1000, 2)
+    assert torch.allclose(a["rotations"].norm(dim=1), torch.ones(1000), atol=1e-5)
+    assert cam["viewmatrix"].shape == (4, 4) and abs(cam["tanfovx"] - np.tan(np.pi / 6)) < 1e-9
+    # camera at (0,0,-5) looking down +z: world origin is 5 in front
+    assert torch.allclose(cam["campos"], torch.tensor([0.0, 0.0, -5.0]), atol=1e-5)
+
+
+def test_oracle_small_scene_invariants():
+    O = H.cpu_oracle()
+    syn = H.synthetic()
+    gs, cam = syn.make_scene(4000, 160, 112, seed=3)
+    bg = torch.tensor([0.2, 0.3, 0.4])
+    st = H.run_cpu_oracle(gs, cam, bg)
+    R = st["num_rendered"]
+    assert R == int(st["tiles_touched"].sum()) and R > 0
+    assert np.all(np.diff(st["keys"].astype(np.uint64)) >= 0)
+    rng = st["ranges"].astype(np.int64)
+    assert int((rng[:, 1] - rng[:, 0]).sum()) == R
+    # stable order: equal keys keep ascending Gaussian id
+    k, v = st["keys"], st["point_list"].astype(np.int64)
+    same = k[1:] == k[:-1]
+    assert np.all(v[1:][same] > v[:-1][same])
+    assert np.all(st["alpha"] <= 1.0 + 1e-5) and np.all(st["alpha"] >= 0)
+    # empty and degenerate inputs
+    e = O.forward(np.zeros((0, 3)), np.zeros((0, 1)), 32, 32, 0.5, 0.5, np.eye(4), np.eye(4), np.zeros(3), np.ones(3), shs=np.zeros((0, 16, 3)),
+                  scales=np.zeros((0, 3)), rotations=np.zeros((0, 4)))
+    assert e["num_rendered"] == 0 and float(np.abs(e["color"]).max()) == 0.0
+
+
+def test_oracle_sort_and_ranges_match_numpy():
+    O = H.cpu_oracle()
+    L = O.lib()
+    rng = np.random.default_rng(0)
+    n = 50_000
+    tiles = rng.integers(0, 300, n).astype(np.uint64)
+    depth = rng.random(n).astype(np.float32) * 10 + 0.3
+    depth[::7] = depth[0]  # ties
+    keys = (tiles << np.uint64(32)) | depth.view(np.uint32).astype(np.uint64)
+    vals = np.arange(n, dtype=np.uint32)
+    ko, vo = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+    L.orc_sort_pairs(ctypes.c_size_t(n), O._p(keys), O._p(ko), O._p(vals), O._p(vo), ctypes.c_int(32 + int(L.orc_higher_msb(ctypes.c_uint32(300)))))
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
+    assert int(L.orc_higher_msb(ctypes.c_uint32(8160))) == 13 and int(L.orc_higher_msb(ctypes.c_uint32(2500))) == 12
+
+
+def test_oracle_knn_matches_bruteforce():
+    O = H.cpu_oracle()
+    rng = np.random.default_rng(1)
+    pts = rng.normal(size=(3000, 3)).astype(np.float32)
+    pts[5] = pts[4]  # duplicate point -> distance 0 counts
+    got = O.knn_dist2(pts)
+    d = ((pts[:, None, :].astype(np.float64) - pts[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d, np.inf)
+    exp = np.sort(d, axis=1)[:, :3].mean(1)
+    assert np.allclose(got, exp, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "pyref_sh_cov.npz")), reason="golden fixture missing")
+def test_oracle_matches_python_reference_fixture():
+    """tests/golden/pyref_sh_cov.npz was produced by importing the reference's own Python (utils/sh_utils.py eval_sh,
+    utils/general_utils.py build_scaling_rotation/strip_symmetric) -- see tests/golden/make_golden_pyref.py."""
+    z = np.load(os.path.join(GOLDEN, "pyref_sh_cov.npz"))
+    O = H.cpu_oracle()
+    cam = {k[4:]: z[k] for k in z.files if k.startswith("cam_")}
+    for deg in range(4):
+        st = O.forward(z["means3D"], z["opacities"], int(cam["W"]), int(cam["H"]), float(cam["tanfovx"]), float(cam["tanfovy"]),
+                       cam["viewmatrix"], cam["projmatrix"], cam["campos"], np.zeros(3), shs=z["shs"], scales=z["scales"],
+                       rotations=z["rotations"], sh_degree=deg)
+        vis = st["radii"] > 0
+        assert vis.sum() > 100
+        assert np.abs(st["rgb"][vis] - z["rgb_deg%d" % deg][vis]).max() <= 2e-6
+        assert np.abs(st["cov3D"][vis] - z["cov3D"][vis]).max() <= 1e-6 * np.abs(z["cov3D"][vis]).max() + 1e-9
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "ref_cuda_small.npz")), reason="golden fixture missing")
+def test_oracle_matches_reference_cuda_fixture():
+    """tests/golden/ref_cuda_small.npz holds outputs of the reference's own CUDA rasterizer (oracle/_ref) run on a B200 on
+    a seeded scene -- see tests/golden/make_golden_refcuda.py. This pins oracle B to the reference."""
+    z = np.load(os.path.join(GOLDEN, "ref_cuda_small.npz"))
+    syn = H.synthetic()
+    P, W, Hh, seed = int(z["P"]), int(z["W"]), int(z["H"]), int(z["seed"])
+    gs, cam = syn.make_scene(P, W, Hh, seed=seed)
+    ug = syn.upstream_grads(W, Hh, seed, with_depth=True, with_segment=True, with_alpha=True)
+    st = H.run_cpu_oracle(gs, cam, torch.from_numpy(z["bg"]), ug)
+    assert (st["radii"] != z["radii"]).mean() <= 2e-4
+    if np.array_equal(st["radii"], z["radii"]):
+        assert st["num_rendered"] == int(z["num_rendered"])
+        assert np.array_equal(st["point_list"], z["point_list"].astype(np.uint32))
+        assert np.array_equal(st["ranges"], z["ranges"].astype(np.uint32))
+        assert (st["n_contrib"] != z["n_contrib"].astype(np.uint32)).mean() <= 1e-3
+        for k in ["color", "depth", "alpha", "segment"]:
+            d = np.abs(st[k] - z[k]).reshape(st[k].shape[0], -1)
+            assert (d > 2e-5).any(0).mean() <= 2e-3, k
+        for k in ["grad_means3D", "grad_means2D", "grad_sh", "grad_segments", "grad_opacities", "grad_scales", "grad_rotations"]:
+            a, b = st["grads"][k], z[k].reshape(st["grads"][k].shape)
+            assert np.quantile(np.abs(a - b), 0.999) <= 1e-3 * np.abs(b).max(), k

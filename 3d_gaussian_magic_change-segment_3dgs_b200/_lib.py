@@ -57,7 +57,7 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 
 # every symbol include/gsr.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
-           "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_set_profiling", "gsr_get_stage_times"]
+           "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times"]
 
 _lib = None
 
@@ -94,6 +94,7 @@ def lib():
     L.gsr_export_state.restype = ctypes.c_int
     L.gsr_export_state.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(GsrState), ctypes.POINTER(GsrStateExport),
                                    ctypes.c_void_p]
+    L.gsr_launch_count.restype = ctypes.c_ulonglong
     L.gsr_set_profiling.restype = None
     L.gsr_set_profiling.argtypes = [ctypes.c_int]
     L.gsr_get_stage_times.restype = ctypes.c_int

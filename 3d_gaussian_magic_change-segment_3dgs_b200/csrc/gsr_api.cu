@@ -10,6 +10,9 @@
 namespace gsr
 {
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...)
 {
@@ -137,6 +140,7 @@ using namespace gsr;
 
 extern "C" int gsr_abi_version(void) { return GSR_ABI_VERSION; }
 extern "C" const char* gsr_last_error(void) { return g_err; }
+extern "C" unsigned long long gsr_launch_count(void) { return gsr::launches(); }
 extern "C" void gsr_set_profiling(int enable) { g_timer.enabled = enable != 0; }
 extern "C" int gsr_get_stage_times(float* ms, const char** names)
 {
@@ -437,10 +441,10 @@ extern "C" int gsr_export_state(int32_t P, int32_t W, int32_t H, const GsrState*
     if (out->rgb) GSR_CUDA(cudaMemsetAsync(out->rgb, 0, (size_t)P * 12, s));
     if (out->clamped) GSR_CUDA(cudaMemsetAsync(out->clamped, 0, (size_t)P * 3, s));
     if (out->tiles_touched) GSR_CUDA(cudaMemsetAsync(out->tiles_touched, 0, (size_t)P * 4, s));
-    export_gaussians_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, g.nblk, *out);
+    export_gaussians_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, g.nblk, *out); count_launches(1);
     GSR_LAUNCHED(s, false, "export_gaussians");
     if ((out->point_list || out->point_keys) && state->num_rendered > 0) {
-        export_lists_kernel<<<T, 256, 0, s>>>(g, (const uint32_t*)state->binning, img.ranges, T, *out);
+        export_lists_kernel<<<T, 256, 0, s>>>(g, (const uint32_t*)state->binning, img.ranges, T, *out); count_launches(1);
         GSR_LAUNCHED(s, false, "export_lists");
     }
     if (out->ranges) GSR_CUDA(cudaMemcpyAsync(out->ranges, img.ranges, (size_t)T * 8, cudaMemcpyDeviceToDevice, s));

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __rest
 int launch_depth_keys(const GeomState& g, const BinState& b, cudaStream_t s)
 {
     if (g.nblk == 0) return 0;
-    depth_keys_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, b.dkeys[0], b.dvals[0]);
+    depth_keys_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, b.dkeys[0], b.dvals[0]); count_launches(1);
     return 0;
 }
 
@@ -108,7 +108,7 @@ int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, c
         GSR_CUDA(cudaMemsetAsync(b.soff, 0, sizeof(uint32_t), s));
         return 0;
     }
-    sorted_tiles_kernel<<<(V + 255) / 256, 256, 0, s>>>(g.rect, sorted_slots, V, b.soff);
+    sorted_tiles_kernel<<<(V + 255) / 256, 256, 0, s>>>(g.rect, sorted_slots, V, b.soff); count_launches(1);
     return exclusive_scan_u32(b.soff, b.soff, V, true, b.scan_part, s);
 }
 
@@ -116,7 +116,7 @@ int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, c
                 uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s)
 {
     if (V == 0 || R == 0) return 0;
-    emit_kernel<<<(V + 255) / 256, 256, 0, s>>>(g.rect, sorted_slots, b.soff, V, grid_x, out_keys, out_vals);
+    emit_kernel<<<(V + 255) / 256, 256, 0, s>>>(g.rect, sorted_slots, b.soff, V, grid_x, out_keys, out_vals); count_launches(1);
     return 0;
 }
 
@@ -124,7 +124,7 @@ int launch_tile_ranges(const uint32_t* sorted_tile_keys, uint32_t R, uint2* rang
 {
     GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), s));
     if (R == 0) return 0;
-    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(sorted_tile_keys, R, ranges);
+    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(sorted_tile_keys, R, ranges); count_launches(1);
     return 0;
 }
 } // namespace gsr

@@ -127,6 +127,7 @@ int check_cuda(cudaError_t e, const char* what);
 // After a kernel launch: always catch launch-configuration errors; in debug mode also synchronise
 // (the reference's CHECK_CUDA, auxiliary.h:166-173).
 int after_launch(cudaStream_t s, bool debug, const char* stage);
+void count_launches(int n); // kernels launched by this library (gsr_launch_count)
 #define GSR_LAUNCHED(stream, debug, stage)                           \
     do {                                                             \
         int _rc = gsr::after_launch((stream), (debug), (stage));     \

@@ -397,24 +397,24 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 int launch_preprocess_fwd(const PreFwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
-    preprocess_fwd_kernel<<<a.g.nblk, PRE_BLOCK, 0, s>>>(a);
+    preprocess_fwd_kernel<<<a.g.nblk, PRE_BLOCK, 0, s>>>(a); count_launches(1);
     return 0;
 }
 int launch_block_offsets(const GeomState& g, cudaStream_t s)
 {
-    block_offsets_kernel<<<1, 1024, 0, s>>>(g);
+    block_offsets_kernel<<<1, 1024, 0, s>>>(g); count_launches(1);
     return 0;
 }
 int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
-    preprocess_bwd_kernel<<<a.g.nblk, PRE_BLOCK, 0, s>>>(a);
+    preprocess_bwd_kernel<<<a.g.nblk, PRE_BLOCK, 0, s>>>(a); count_launches(1);
     return 0;
 }
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s)
 {
     if (P <= 0) return 0;
-    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present); count_launches(1);
     return 0;
 }
 } // namespace gsr

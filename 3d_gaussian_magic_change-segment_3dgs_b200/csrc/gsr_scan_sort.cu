@@ -189,8 +189,8 @@ int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, bool write
         return 0;
     }
     const uint32_t nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
-    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, partials);
-    scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, partials, out, write_total ? 1 : 0);
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, partials); count_launches(1);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, partials, out, write_total ? 1 : 0); count_launches(1);
     return 0;
 }
 
@@ -214,10 +214,10 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits
     for (int p = 0; p < passes; p++) {
         const int shift = p * digit_bits;
         const uint32_t mask = bins - 1;
-        radix_hist_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], n, shift, mask, nb, hist);
+        radix_hist_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], n, shift, mask, nb, hist); count_launches(1);
         int rc = exclusive_scan_u32(hist, hist, (uint32_t)hwords, false, partials, s);
         if (rc) return rc;
-        radix_scatter_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, mask, nb, hist);
+        radix_scatter_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, mask, nb, hist); count_launches(1);
         cur ^= 1;
     }
     return cur;

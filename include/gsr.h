@@ -155,6 +155,9 @@ int gsr_export_state(int32_t P, int32_t image_width, int32_t image_height, const
 
 /* Per-stage device timings (ms) of the most recent gsr_forward / gsr_backward on this thread when
  * gsr_set_profiling(1) is active (adds cudaEvent records; used by bench.py for the roofline block). */
+/* Number of CUDA kernels this library has launched so far in this process (all threads). */
+unsigned long long gsr_launch_count(void);
+
 #define GSR_STAGE_COUNT 16
 void gsr_set_profiling(int enable);
 int gsr_get_stage_times(float* ms /*[GSR_STAGE_COUNT]*/, const char** names /*[GSR_STAGE_COUNT]*/);

@@ -61,7 +61,7 @@ def _f(v):
 
 def forward(means3D, opacities, W, H, tanfovx, tanfovy, viewmatrix, projmatrix, campos, bg, shs=None, colors_precomp=None,
             segments=None, scales=None, rotations=None, cov3D_precomp=None, sh_degree=3, scale_modifier=1.0,
-            prefiltered=False):
+            prefiltered=False, row_stride=1, row_offset=0):
     """All array arguments are numpy (any float dtype; converted to fp32). viewmatrix/projmatrix are the 16 floats
     exactly as the reference receives them (transposed, i.e. column-major for the kernels)."""
     L = lib()
@@ -118,8 +118,10 @@ def forward(means3D, opacities, W, H, tanfovx, tanfovy, viewmatrix, projmatrix, 
     feats = colors_precomp if colors_precomp is not None else st["rgb"]
     n_contrib = np.zeros(N, np.uint32)
     L.orc_render_forward(_i(W), _i(H), _i(S), _p(ranges), _p(vs), _p(st["means2D"]), _p(feats), _p(segments), _p(st["depths"]),
-                         _p(st["conic_opacity"]), _p(bg), _p(color), _p(segment), _p(depth), _p(alpha), _p(n_contrib))
+                         _p(st["conic_opacity"]), _p(bg), _p(color), _p(segment), _p(depth), _p(alpha), _p(n_contrib),
+                         _i(row_stride), _i(row_offset))
     st["n_contrib"] = n_contrib
+    st["_rows"] = (row_stride, row_offset)
     st["_inputs"] = dict(means3D=means3D, opacities=opacities, shs=shs, colors_precomp=colors_precomp, segments=segments,
                          scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp, view=view, proj=proj, campos=campos,
                          bg=bg, tanfovx=tanfovx, tanfovy=tanfovy, scale_modifier=scale_modifier)
@@ -151,7 +153,7 @@ def backward(st, grad_color, grad_depth=None, grad_alpha=None, grad_segment=None
     L.orc_render_backward(_i(W), _i(H), _i(S), _p(st["ranges"]), _p(st["point_list"]), _p(inp["bg"]), _p(st["means2D"]),
                           _p(st["conic_opacity"]), _p(feats), _p(inp["segments"]), _p(st["depths"]), _p(st["alpha"]),
                           _p(st["n_contrib"]), _p(gc), _p(gs), _p(gd), _p(ga), _p(dmean2D), _p(dconic), _p(dopacity), _p(dcolors),
-                          _p(dsegments), _p(ddepths))
+                          _p(dsegments), _p(ddepths), _i(st.get("_rows", (1, 0))[0]), _i(st.get("_rows", (1, 0))[1]))
     cov3Ds = inp["cov3D_precomp"] if inp["cov3D_precomp"] is not None else st["cov3D"]
     m2, cn = dmean2D.astype(np.float32), dconic.astype(np.float32)
     dc, dd = dcolors.astype(np.float32), ddepths.astype(np.float32)

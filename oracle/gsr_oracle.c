@@ -353,17 +353,19 @@ void orc_identify_tile_ranges(size_t L, const uint64_t* keys, int T, uint32_t* r
  * the block-wide early exit (:317-319) only stops work once every pixel is done, so per-pixel
  * sequential evaluation is equivalent. `features` is colors_precomp or the preprocess rgb (:325).
  * S = number of segment channels (reference NUM_CLASS = 2); segments may be NULL when S == 0.
+ * row_stride > 1 restricts the work to tile rows with row % row_stride == row_offset (bench.py's bounded CPU sample).
  */
 void orc_render_forward(int W, int H, int S, const uint32_t* ranges, const uint32_t* point_list, const float* means2D,
                         const float* features, const float* segments, const float* depths, const float* conic_opacity,
                         const float* bg, float* out_color, float* out_segment, float* out_depth, float* out_alpha,
-                        uint32_t* n_contrib)
+                        uint32_t* n_contrib, int row_stride, int row_offset)
 {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const size_t HW = (size_t)H * W;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int tile = 0; tile < gx * gy; tile++) {
         const int tx = tile % gx, ty = tile / gx;
+        if (row_stride > 1 && ty % row_stride != row_offset) continue; /* bounded sample for the CPU baseline timing */
         const uint32_t r0 = ranges[2 * (size_t)tile], r1 = ranges[2 * (size_t)tile + 1];
         for (int ly = 0; ly < TILE; ly++)
             for (int lx = 0; lx < TILE; lx++) {
@@ -418,7 +420,7 @@ void orc_render_backward(int W, int H, int S, const uint32_t* ranges, const uint
                          const float* depths, const float* alphas, const uint32_t* n_contrib, const float* dL_dpixels,
                          const float* dL_dpixels_segments, const float* dL_dpixel_depths, const float* dL_dalphas,
                          double* dmean2D, double* dconic, double* dopacity, double* dcolors, double* dsegments,
-                         double* ddepths)
+                         double* ddepths, int row_stride, int row_offset)
 {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const size_t HW = (size_t)H * W;
@@ -426,6 +428,7 @@ void orc_render_backward(int W, int H, int S, const uint32_t* ranges, const uint
 #pragma omp parallel for schedule(dynamic, 1)
     for (int tile = 0; tile < gx * gy; tile++) {
         const int tx = tile % gx, ty = tile / gx;
+        if (row_stride > 1 && ty % row_stride != row_offset) continue;
         const uint32_t r0 = ranges[2 * (size_t)tile], r1 = ranges[2 * (size_t)tile + 1];
         for (int ly = 0; ly < TILE; ly++)
             for (int lx = 0; lx < TILE; lx++) {

@@ -44,8 +44,8 @@ struct StageTimer
     bool enabled = false;
     std::vector<cudaEvent_t> ev;
     std::vector<const char*> names;
-    float ms[GSR_STAGE_COUNT];
-    const char* out_names[GSR_STAGE_COUNT];
+    float ms[GSR_STAGE_COUNT] = {0};
+    const char* out_names[GSR_STAGE_COUNT] = {nullptr};
     int count = 0;
 
     void begin(cudaStream_t s)
@@ -78,7 +78,9 @@ struct StageTimer
         }
     }
 };
-static thread_local StageTimer g_timer;
+// process-global on purpose: autograd runs gsr_backward on its own worker thread, bench.py reads the times from the main
+// thread. Profiling mode is a single-stream diagnostic (bench.py), not meant for concurrent callers.
+static StageTimer g_timer;
 static const int kBwdFirstSlot = 10;
 
 static int ceil_log2(uint32_t v)
@@ -169,7 +171,10 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
     const uint32_t T = (uint32_t)gx * (uint32_t)gy;
     const size_t N = (size_t)W * H;
 
-    g_timer.count = 0;
+    if (g_timer.enabled) {
+        g_timer.count = 0;
+        for (int i = 0; i < GSR_STAGE_COUNT; i++) { g_timer.ms[i] = 0.f; g_timer.out_names[i] = nullptr; }
+    }
     g_timer.begin(s);
 
     // ---- state buffers whose size is known up front ----

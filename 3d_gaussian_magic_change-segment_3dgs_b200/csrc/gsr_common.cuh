@@ -32,6 +32,7 @@ struct GeomState
     ushort4* rect;       // [slots] tile rectangle {xmin, ymin, xmax, ymax} (auxiliary.h:46-56)
     uint32_t* slot_gid;  // [slots] Gaussian id of the slot
     uint8_t* clamped;    // [slots] bit c set <=> SH colour channel c was clamped (forward.cu:67-69)
+    uint32_t* vis_slot;  // [slots] slot of the r-th visible Gaussian (Gaussian-id order), r < V
     uint32_t* blk_count; // [nblk] visible Gaussians per slot-block
     uint32_t* blk_offset;// [nblk] exclusive scan of blk_count
     uint32_t nblk;
@@ -77,6 +78,7 @@ inline size_t geom_layout(char* base, int P, GeomState& g)
     carve(p, g.rect, (size_t)g.slots);
     carve(p, g.slot_gid, (size_t)g.slots);
     carve(p, g.clamped, (size_t)g.slots);
+    carve(p, g.vis_slot, (size_t)g.slots);
     carve(p, g.blk_count, (size_t)g.nblk);
     carve(p, g.blk_offset, (size_t)g.nblk + 1);
     return (size_t)(p - base) + 256;

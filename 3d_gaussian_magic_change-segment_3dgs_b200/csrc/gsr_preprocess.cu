@@ -182,19 +182,21 @@ __global__ void __launch_bounds__(1024) block_offsets_kernel(GeomState g)
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// One thread per VISIBLE Gaussian (rank r in Gaussian-id order -> slot -> id): the heavy chain rule runs on dense warps
+// (only ~20% of the Gaussians of a view are visible; a thread-per-Gaussian layout would execute it with ~80% idle lanes).
 __global__ void __launch_bounds__(PRE_BLOCK) preprocess_bwd_kernel(const PreBwdArgs a)
 {
     __shared__ float s_view[16], s_proj[16];
-    __shared__ uint32_t s_warp[8];
     if (threadIdx.x < 16) {
         s_view[threadIdx.x] = a.view[threadIdx.x];
         s_proj[threadIdx.x] = a.proj[threadIdx.x];
     }
-    const int idx = blockIdx.x * PRE_BLOCK + threadIdx.x;
-    const bool visible = idx < a.P && a.radii[idx] > 0;
-    uint32_t nvis;
-    const uint32_t rank = block_rank_256(visible, s_warp, nvis); // contains the __syncthreads for s_view/s_proj
-    if (idx >= a.P) return;
+    __syncthreads();
+    const uint32_t r = blockIdx.x * PRE_BLOCK + threadIdx.x;
+    if (r >= a.g.counters[CNT_VISIBLE]) return;
+    const uint32_t slot = a.g.vis_slot[r];
+    const int idx = (int)a.g.slot_gid[slot];
+    const bool visible = true;
 
     float3 dL_dmean = {0.f, 0.f, 0.f};
     float2 dL_dmean2D = {0.f, 0.f};
@@ -209,7 +211,6 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_bwd_kernel(const PreBwdA
     for (int k = 0; k < 16; k++) dsh[k] = {0.f, 0.f, 0.f};
 
     if (visible) {
-        const uint32_t slot = blockIdx.x * PRE_BLOCK + rank;
         const float4* gr = reinterpret_cast<const float4*>(a.grad_rec + (size_t)slot * GRAD_REC_FLOATS);
         const float4 g0 = gr[0]; // dcolor.rgb, ddepth
         const float4 g1 = gr[1]; // dseg0, dseg1, dmean2D.x, dmean2D.y
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_bwd_kernel(const PreBwdA
         if (a.scales != nullptr) cov3d_backward(sc, a.scale_modifier, q, dL_dcov3D, dL_dscale, dL_drot);
     }
 
-    // ---- dense gradient rows: every row written exactly once, zeros for invisible Gaussians ----
+    // ---- gradient rows of this visible Gaussian (rows of invisible ones are zero-filled by zero_invisible_rows_kernel) ----
     const size_t i = (size_t)idx;
     if (a.out.dL_dmeans3D) {
         a.out.dL_dmeans3D[3 * i + 0] = dL_dmean.x;
@@ -383,6 +384,48 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_bwd_kernel(const PreBwdA
     }
 }
 
+// Warp w of the grid owns Gaussians [32w, 32w+32). For every output array the warp's rows form one contiguous span of
+// 32*width floats; lanes stride over it and store zeros where the owning Gaussian is invisible: fully coalesced streaming
+// stores, every invisible row written exactly once (replaces the reference's 11 torch::zeros fills of ALL rows,
+// rasterize_points.cu:166-177).
+template <typename T>
+__device__ __forceinline__ void zero_rows(T* __restrict__ base, uint32_t first, uint32_t units_per_row, uint32_t nrows, uint32_t invisible,
+                                          uint32_t lane, T zero)
+{
+    if (base == nullptr) return;
+    T* span = base + (size_t)first * units_per_row;
+    const uint32_t total = nrows * units_per_row;
+    for (uint32_t f = lane; f < total; f += 32) {
+        const uint32_t row = f / units_per_row;
+        if ((invisible >> row) & 1u) span[f] = zero;
+    }
+}
+
+__global__ void __launch_bounds__(PRE_BLOCK) zero_invisible_rows_kernel(int P, int M, int S, const int32_t* __restrict__ radii, GsrParamGrads out)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t first = (blockIdx.x * PRE_BLOCK + threadIdx.x) & ~31u;
+    if (first >= (uint32_t)P) return;
+    const uint32_t idx = first + lane;
+    const bool inv = idx < (uint32_t)P && !(radii[idx] > 0);
+    const uint32_t invisible = __ballot_sync(0xffffffffu, inv);
+    if (invisible == 0) return;
+    const uint32_t nrows = min(32u, (uint32_t)P - first);
+    const float4 z4 = {0.f, 0.f, 0.f, 0.f};
+    if (out.dL_dsh) {
+        if ((M * 3) % 4 == 0) zero_rows(reinterpret_cast<float4*>(out.dL_dsh), first, (uint32_t)(M * 3) / 4, nrows, invisible, lane, z4);
+        else zero_rows(out.dL_dsh, first, (uint32_t)(M * 3), nrows, invisible, lane, 0.f);
+    }
+    zero_rows(out.dL_dmeans3D, first, 3u, nrows, invisible, lane, 0.f);
+    zero_rows(out.dL_dmeans2D, first, 3u, nrows, invisible, lane, 0.f);
+    zero_rows(out.dL_dopacity, first, 1u, nrows, invisible, lane, 0.f);
+    zero_rows(out.dL_dcolors, first, 3u, nrows, invisible, lane, 0.f);
+    if (S > 0) zero_rows(out.dL_dsegments, first, (uint32_t)S, nrows, invisible, lane, 0.f);
+    zero_rows(out.dL_dscales, first, 3u, nrows, invisible, lane, 0.f);
+    zero_rows(reinterpret_cast<float4*>(out.dL_drotations), first, 1u, nrows, invisible, lane, z4);
+    zero_rows(out.dL_dcov3D, first, 6u, nrows, invisible, lane, 0.f);
+}
+
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
                                                            uint8_t* __restrict__ present)
 {
@@ -408,6 +451,8 @@ int launch_block_offsets(const GeomState& g, cudaStream_t s)
 int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
+    // streaming zero rows for the invisible Gaussians, dense compute rows for the visible ones (disjoint rows)
+    zero_invisible_rows_kernel<<<(a.P + PRE_BLOCK - 1) / PRE_BLOCK, PRE_BLOCK, 0, s>>>(a.P, a.M, a.S, a.radii, a.out); count_launches(1);
     preprocess_bwd_kernel<<<a.g.nblk, PRE_BLOCK, 0, s>>>(a); count_launches(1);
     return 0;
 }

@@ -1,0 +1,78 @@
+"""Multi-view data-parallel step: the only way this path shards.
+
+Gaussian parameters are REPLICATED on every rank; the B views of a step are split `views[rank::world]`; each rank
+rasterizes its own cameras (forward + backward through the drop-in API, each view's loss pre-scaled by 1/B) and the
+parameter gradients are summed over ranks with NCCL (`torch.distributed`, one process per GPU). Densification
+statistics are reduced the same way, so every rank can apply the identical densify/prune decision:
+
+    xyz_gradient_accum += || dL/d(mean2D)[:, :2] ||   per view, visible Gaussians only   (scene/gaussian_model.py:523-526)
+    denom              += visible                                                         (same)
+    max_radii2D         = max(max_radii2D, radii)      visible Gaussians only             (train.py:172)
+
+The per-view norm is taken BEFORE summing across views, which is what sequential single-view training accumulates.
+The reference itself is single-view / single-GPU; this driver is new behaviour layered on the unchanged rasterizer API.
+Nothing here depends on CUDA: with the `gloo` backend and an injected render function it runs on CPU (tests/).
+"""
+import torch
+
+LEAVES = ["means3D", "shs", "segments", "opacities", "scales", "rotations"]  # 3+48+2+1+3+4 = 61 floats per Gaussian
+
+
+def shard_views(num_views, rank, world):
+    """Indices of the views this rank renders."""
+    return list(range(rank, num_views, world))
+
+
+class DensificationStats:
+    def __init__(self, P, device):
+        self.xyz_gradient_accum = torch.zeros(P, 1, device=device)
+        self.denom = torch.zeros(P, 1, device=device)
+        self.max_radii2D = torch.zeros(P, device=device)
+
+    def add_view(self, viewspace_grad, radii):
+        vis = radii > 0
+        self.max_radii2D[vis] = torch.max(self.max_radii2D[vis], radii[vis].to(self.max_radii2D.dtype))
+        self.xyz_gradient_accum[vis] += torch.norm(viewspace_grad[vis, :2], dim=-1, keepdim=True)
+        self.denom[vis] += 1
+
+    def allreduce(self, dist, group=None):
+        dist.all_reduce(self.xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.denom, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+def multiview_step(leaves, cams, render_fn, loss_fn, rank=0, world=1, dist=None, group=None, stats=None):
+    """One batched step.
+
+    leaves    dict name -> leaf tensor (requires_grad) of the replicated Gaussians (any subset of LEAVES)
+    cams      list of the step's B cameras (same list on every rank)
+    render_fn (leaves, cam) -> dict with at least "render", "viewspace_points", "radii" (gaussian_renderer.render()'s dict)
+    loss_fn   (render dict, cam, view_index) -> scalar loss of that view
+    Returns the summed loss over ALL views (all-reduced). Gradients end up in leaf.grad, identical on all ranks.
+    """
+    B = len(cams)
+    for t in leaves.values():
+        t.grad = None
+    total = None
+    for vi in shard_views(B, rank, world):
+        out = render_fn(leaves, cams[vi])
+        loss = loss_fn(out, cams[vi], vi) / B
+        loss.backward()
+        if stats is not None:
+            vp = out["viewspace_points"]
+            # the densification criterion uses the gradient of the UNscaled per-view loss
+            stats.add_view(vp.grad * B if vp.grad is not None else torch.zeros_like(vp), out["radii"])
+        total = loss.detach() if total is None else total + loss.detach()
+    first = next(iter(leaves.values()))
+    if total is None:
+        total = torch.zeros((), device=first.device)
+    if dist is not None and world > 1:
+        for name in leaves:
+            t = leaves[name]
+            if t.grad is None:  # a rank with no views still takes part in the collective
+                t.grad = torch.zeros_like(t)
+            dist.all_reduce(t.grad, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        if stats is not None:
+            stats.allreduce(dist, group)
+    return total

@@ -1,0 +1,64 @@
+"""GPU tests of the rebuilt simple-knn (distCUDA2) against the reference's own CUDA build (oracle A, bit-exact expected:
+exact 3-NN with the reference's distance expression) and the CPU oracle / brute force."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _points(n, seed, kind="uniform"):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "uniform":
+        return torch.rand(n, 3, generator=g) * 12 - 6
+    if kind == "clustered":
+        c = torch.randn(20, 3, generator=g) * 5
+        return c[torch.randint(0, 20, (n,), generator=g)] + torch.randn(n, 3, generator=g) * 0.05
+    if kind == "planar":  # degenerate axis: all z equal
+        p = torch.rand(n, 3, generator=g)
+        p[:, 2] = 0.25
+        return p
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("n,kind", [(1, "uniform"), (3, "uniform"), (4, "uniform"), (63, "uniform"), (1000, "uniform"), (100_000, "uniform"),
+                                    (50_000, "clustered"), (20_000, "planar")])
+def test_knn_vs_cpu_oracle(n, kind):
+    Pk = H.pkg()
+    pts = _points(n, 1, kind)
+    if n >= 100:
+        pts[7] = pts[3]  # duplicate: distance 0 counts, self is excluded by index
+    got = Pk.distCUDA2(pts.cuda()).cpu().numpy()
+    exp = H.cpu_oracle().knn_dist2(pts.numpy())
+    if n < 4:
+        assert np.all(np.isinf(got)) and np.all(np.isinf(exp))
+        return
+    assert np.allclose(got, exp, rtol=1e-6, atol=0), np.abs(got - exp).max()
+
+
+def test_knn_vs_reference_cuda_bit_exact():
+    C = H.ref_knn()
+    if C is None:
+        pytest.skip("oracle/_ref not built")
+    Pk = H.pkg()
+    for n, kind, seed in [(100_000, "uniform", 2), (300_000, "clustered", 3), (1_000_000, "uniform", 4)]:
+        pts = _points(n, seed, kind).cuda()
+        got = Pk.distCUDA2(pts)
+        ref = C.distCUDA2(pts)
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref), (n, kind, float((got - ref).abs().max()))
+
+
+def test_knn_full_size_properties():
+    """6M points (BASELINE size): positive, finite, and equal to brute force on a random subset of queries."""
+    Pk = H.pkg()
+    pts = _points(6_000_000, 5).cuda()
+    got = Pk.distCUDA2(pts)
+    assert torch.isfinite(got).all() and bool((got >= 0).all())
+    idx = torch.randint(0, pts.shape[0], (64,), device="cuda")
+    d = ((pts[idx][:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    d[torch.arange(64), idx] = float("inf")
+    exp = d.topk(3, dim=1, largest=False).values.mean(1)
+    assert torch.allclose(got[idx], exp, rtol=1e-5, atol=0)

@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(256) knn_search_kernel(int P, const float4* __
             const float4 c = s_leaf[w][j];
             if (first + j == qi) continue; // self, excluded by index (duplicates at distance 0 count)
             const float3 d = {c.x - q.x, c.y - q.y, c.z - q.z};
-            const float dist = d.x * d.x + d.y * d.y + d.z * d.z;
+            // d.x*d.x + d.y*d.y + d.z*d.z exactly as nvcc contracts it in the reference's updateKBest (SASS of boxMeanDist:
+            // FMUL dy,dy ; FFMA dx,dx ; FFMA dz,dz). Spelled with intrinsics so the association cannot drift with context.
+            const float dist = __fmaf_rn(d.z, d.z, __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y)));
             keep_3_best(dist, best);
         }
     };

@@ -83,6 +83,25 @@ struct StageTimer
 static StageTimer g_timer;
 static const int kBwdFirstSlot = 10;
 
+// Pinned landing zone + event for the forward's counter read-back, one per (thread, device).
+struct HostSync
+{
+    uint32_t* pinned = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+static HostSync* host_sync()
+{
+    static thread_local HostSync cache[64];
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice") || dev < 0 || dev >= 64) return nullptr;
+    HostSync& h = cache[dev];
+    if (!h.pinned) {
+        if (check_cuda(cudaHostAlloc((void**)&h.pinned, 64, cudaHostAllocPortable), "cudaHostAlloc")) return nullptr;
+        if (check_cuda(cudaEventCreateWithFlags(&h.ev, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    }
+    return &h;
+}
+
 static int ceil_log2(uint32_t v)
 {
     int b = 0;
@@ -209,10 +228,24 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
     GSR_LAUNCHED(s, debug, "block_offsets");
     g_timer.mark(s, "preprocess_fwd");
 
-    // ---- the one host synchronisation: V and R size the binning state (reference: rasterizer_impl.cu:285) ----
-    uint32_t counters[8];
-    GSR_CUDA(cudaMemcpyAsync(counters, g.counters, sizeof(counters), cudaMemcpyDeviceToHost, s));
-    GSR_CUDA(cudaStreamSynchronize(s));
+    // ---- the one host synchronisation: V and R size the binning state (reference: rasterizer_impl.cu:285). The counters are
+    // copied to pinned memory behind an event, and the depth sort -- whose buffers live in the geometry state with capacity P
+    // and whose element count V is read on the device -- is enqueued BEFORE waiting, so the GPU keeps working while the host
+    // round-trips, allocates the binning state and enqueues the rest.
+    HostSync* hs = host_sync();
+    if (!hs) return GSR_ERR_CUDA;
+    GSR_CUDA(cudaMemcpyAsync(hs->pinned, g.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaEventRecord(hs->ev, s));
+
+    launch_depth_keys(g, s);
+    GSR_LAUNCHED(s, debug, "depth_keys");
+    int dres = radix_sort_pairs(g.dkeys, g.dvals, g.slots, 32, g.dhist, g.dhist_words, s, g.counters + CNT_VISIBLE);
+    if (dres < 0) return dres;
+    GSR_LAUNCHED(s, debug, "depth_sort");
+    const uint32_t* sorted_slots = g.dvals[dres];
+
+    GSR_CUDA(cudaEventSynchronize(hs->ev));
+    const uint32_t* counters = hs->pinned;
     if (counters[CNT_ERROR] & 1u) {
         set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
         return GSR_ERR_PREFILTERED;
@@ -234,14 +267,6 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
         return GSR_ERR_ALLOC;
     }
     bin_layout(bin_base, V, R, b);
-
-    // ---- depth order of the visible Gaussians ----
-    launch_depth_keys(g, b, s);
-    GSR_LAUNCHED(s, debug, "depth_keys");
-    int dres = radix_sort_pairs(b.dkeys, b.dvals, V, 32, b.hist, b.hist_words, s);
-    if (dres < 0) return dres;
-    GSR_LAUNCHED(s, debug, "depth_sort");
-    const uint32_t* sorted_slots = b.dvals[dres];
     g_timer.mark(s, "depth_sort");
 
     // ---- instances in depth order, then stable sort by tile ----

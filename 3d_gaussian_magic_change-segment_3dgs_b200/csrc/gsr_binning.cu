@@ -125,10 +125,10 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __rest
 }
 } // namespace
 
-int launch_depth_keys(const GeomState& g, const BinState& b, cudaStream_t s)
+int launch_depth_keys(const GeomState& g, cudaStream_t s)
 {
     if (g.nblk == 0) return 0;
-    depth_keys_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, b.dkeys[0], b.dvals[0]); count_launches(1);
+    depth_keys_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, g.dkeys[0], g.dvals[0]); count_launches(1);
     return 0;
 }
 

@@ -35,6 +35,10 @@ struct GeomState
     uint32_t* vis_slot;  // [slots] slot of the r-th visible Gaussian (Gaussian-id order), r < V
     uint32_t* blk_count; // [nblk] visible Gaussians per slot-block
     uint32_t* blk_offset;// [nblk] exclusive scan of blk_count
+    uint32_t* dkeys[2];  // [slots] depth bits of the visible Gaussians (ping-pong), first V used
+    uint32_t* dvals[2];  // [slots] their slots (ping-pong)
+    uint32_t* dhist;     // depth-sort histograms + scan partials
+    size_t dhist_words;
     uint32_t nblk;
     uint32_t slots;      // nblk * PRE_BLOCK
 };
@@ -44,8 +48,6 @@ struct BinState
     uint32_t* point_list; // [R] final per-tile lists (slots), depth-sorted; MUST be first (gsr_backward relies on offset 0)
     uint32_t* vals_alt;   // [R]
     uint32_t* tkeys[2];   // [R] tile ids (ping-pong)
-    uint32_t* dkeys[2];   // [V] depth bits (ping-pong)
-    uint32_t* dvals[2];   // [V] slots (ping-pong)
     uint32_t* soff;       // [V+1] exclusive scan of tiles_touched in depth order
     uint32_t* hist;       // radix block histograms followed by their scan partials
     size_t hist_words;
@@ -57,6 +59,9 @@ struct ImgState
     uint32_t* n_contrib; // [H*W]
     uint2* ranges;       // [T]
 };
+
+constexpr int RADIX_ITEMS = 4096;  // keys per radix CTA (256 threads x 16)
+constexpr int SCAN_ITEMS = 2048;   // items per scan CTA (256 threads x 8)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -81,11 +86,16 @@ inline size_t geom_layout(char* base, int P, GeomState& g)
     carve(p, g.vis_slot, (size_t)g.slots);
     carve(p, g.blk_count, (size_t)g.nblk);
     carve(p, g.blk_offset, (size_t)g.nblk + 1);
+    for (int i = 0; i < 2; i++) {
+        carve(p, g.dkeys[i], (size_t)g.slots);
+        carve(p, g.dvals[i], (size_t)g.slots);
+    }
+    const size_t nb = ((size_t)g.slots + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    const size_t h = 256 * (nb + 1);
+    g.dhist_words = h + (h + SCAN_ITEMS - 1) / SCAN_ITEMS + 64;
+    carve(p, g.dhist, g.dhist_words);
     return (size_t)(p - base) + 256;
 }
-
-constexpr int RADIX_ITEMS = 4096;  // keys per radix CTA (256 threads x 16)
-constexpr int SCAN_ITEMS = 2048;   // items per scan CTA (256 threads x 8)
 
 inline size_t bin_layout(char* base, size_t V, size_t R, BinState& b)
 {
@@ -94,10 +104,6 @@ inline size_t bin_layout(char* base, size_t V, size_t R, BinState& b)
     carve(p, b.vals_alt, R);
     carve(p, b.tkeys[0], R);
     carve(p, b.tkeys[1], R);
-    carve(p, b.dkeys[0], V);
-    carve(p, b.dkeys[1], V);
-    carve(p, b.dvals[0], V);
-    carve(p, b.dvals[1], V);
     carve(p, b.soff, V + 1);
     size_t n = R > V ? R : V;
     size_t nb = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
@@ -207,7 +213,7 @@ struct RenderArgs
 int launch_preprocess_fwd(const PreFwdArgs& a, cudaStream_t s);
 int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
 int launch_block_offsets(const GeomState& g, cudaStream_t s);
-int launch_depth_keys(const GeomState& g, const BinState& b, cudaStream_t s);
+int launch_depth_keys(const GeomState& g, cudaStream_t s);
 int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, const uint32_t* sorted_slots, cudaStream_t s);
 int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, int grid_x,
                 uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s);
@@ -219,7 +225,9 @@ int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t*
 // exclusive scan of n u32 values (in may alias out); writes the grand total to out[n] when write_total.
 int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, bool write_total, uint32_t* partials, cudaStream_t s);
 // stable LSD radix sort of (key,val) pairs on key bits [0,nbits). Result lands in keys[res]/vals[res]; returns res (0/1) or <0.
-int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* hist, size_t hist_words, cudaStream_t s);
+// With n_dev != nullptr, n is a CAPACITY (it sizes the grid and the histogram) and the element count is read on the device.
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* hist, size_t hist_words, cudaStream_t s,
+                     const uint32_t* n_dev = nullptr);
 int radix_num_passes(int nbits);
 
 int knn_run(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t s);

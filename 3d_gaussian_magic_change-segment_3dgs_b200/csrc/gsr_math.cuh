@@ -241,10 +241,25 @@ __device__ __forceinline__ float dot3(const V3& a, const V3& b)
     return t.x + t.y + t.z;
 }
 
-// Backward of sh_to_rgb (backward.cu:20-139). sh: this Gaussian's coefficients; dL_dsh_row: its [M][3] output row
-// (written for k < (deg+1)^2 only; the caller zero-fills the rest). Returns the mean-gradient contribution.
+// Backward of sh_to_rgb (backward.cu:20-139). sh: this Gaussian's coefficients; dL_dsh: its [M][3] output row in global
+// memory (may be null), written for k < (deg+1)^2 only; the caller zero-fills the rest. Returns the mean-gradient
+// contribution. Rows are stored as they are produced (like the reference) instead of being held in 48 registers.
+struct ShRowWriter
+{
+    V3* row;
+    struct Ref
+    {
+        V3* p;
+        __device__ __forceinline__ void operator=(const V3& v) const
+        {
+            if (p) *p = v;
+        }
+    };
+    __device__ __forceinline__ Ref operator[](int k) const { return Ref{row ? row + k : nullptr}; }
+};
+
 __device__ __forceinline__ float3 sh_backward(int deg, const float3& pos, const float3& campos, const V3* __restrict__ sh,
-                                              unsigned clamp_bits, V3 dL_dRGB, V3* __restrict__ dL_dsh)
+                                              unsigned clamp_bits, V3 dL_dRGB, ShRowWriter dL_dsh)
 {
     V3 dir_orig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
     const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);

@@ -113,10 +113,12 @@ constexpr int RADIX_PER_THREAD = RADIX_ITEMS / RADIX_THREADS; // 16
 constexpr int RADIX_WARP_ITEMS = RADIX_ITEMS / 8;             // 512 consecutive keys per warp
 
 // Per-CTA digit histogram, written digit-major: hist[d * nblocks + block].
-__global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t mask,
-                                                                   uint32_t nblocks, uint32_t* __restrict__ hist)
+// n_dev != nullptr: the element count lives in device memory (grid sized for a capacity, extra CTAs see no keys).
+__global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ n_dev,
+                                                                   int shift, uint32_t mask, uint32_t nblocks, uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t s_hist[256];
+    if (n_dev) n = *n_dev;
     s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * RADIX_ITEMS;
@@ -130,18 +132,29 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_
 }
 
 // Stable scatter. Warp w of the CTA owns keys [w*512, w*512+512) of the CTA tile and walks them in order, 32 at a
-// time; ranks inside a 32-key step come from match.any, ranks across steps / warps / CTAs from counters.
+// time; ranks inside a 32-key step come from match.any, ranks across steps / warps from shared counters. Pairs are first
+// placed at their rank INSIDE the CTA tile in shared memory (digit-major), then written out by consecutive threads, so
+// every digit run of the tile is one contiguous, coalesced burst (a direct scatter issues 32 unrelated 4-byte stores per
+// warp instruction).
 __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                       uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
-                                                                      int shift, uint32_t mask, uint32_t nblocks,
+                                                                      const uint32_t* __restrict__ n_dev, int shift, uint32_t mask, uint32_t nblocks,
                                                                       const uint32_t* __restrict__ offsets /* scanned hist */)
 {
     __shared__ uint32_t s_cnt[8][256];
+    __shared__ uint32_t s_gbase[256];
+    __shared__ uint32_t s_keys[RADIX_ITEMS];
+    __shared__ uint32_t s_vals[RADIX_ITEMS];
+    __shared__ uint32_t s_warp[8];
+    if (n_dev) n = *n_dev;
+    const uint32_t tile_base = blockIdx.x * RADIX_ITEMS;
+    if (tile_base >= n) return;
+    const uint32_t tile_n = min((uint32_t)RADIX_ITEMS, n - tile_base);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 8 * 256; i += RADIX_THREADS) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
 
-    const uint32_t wbase = blockIdx.x * RADIX_ITEMS + warp * RADIX_WARP_ITEMS;
+    const uint32_t wbase = tile_base + warp * RADIX_WARP_ITEMS;
     uint32_t key[RADIX_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < RADIX_PER_THREAD; k++) {
@@ -150,15 +163,33 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint
         if (i < n) atomicAdd(&s_cnt[warp][(key[k] >> shift) & mask], 1u);
     }
     __syncthreads();
-    // turn per-warp counts into global base positions: offsets[d][block] + counts of earlier warps
+    // digit d (thread d): counts of the 8 warps -> exclusive over warps; tile total per digit -> exclusive over digits
+    uint32_t tot = 0;
+    uint32_t wpre[8];
     if (threadIdx.x <= mask) {
-        uint32_t run = offsets[threadIdx.x * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < 8; w++) {
-            const uint32_t c = s_cnt[w][threadIdx.x];
-            s_cnt[w][threadIdx.x] = run;
-            run += c;
+            wpre[w] = tot;
+            tot += s_cnt[w][threadIdx.x];
         }
+    }
+    // block-wide exclusive scan of `tot` over the 256 threads
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t dstart = incl - tot;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++)
+        if (w < warp) dstart += s_warp[w];
+    if (threadIdx.x <= mask) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) s_cnt[w][threadIdx.x] = dstart + wpre[w]; // rank base inside the tile
+        s_gbase[threadIdx.x] = offsets[threadIdx.x * nblocks + blockIdx.x] - dstart;
     }
     __syncthreads();
 #pragma unroll
@@ -175,9 +206,16 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint
         if (valid && rank == 0) s_cnt[warp][d] += __popc(peers);
         __syncwarp();
         if (valid) {
-            keys_out[pos] = key[k];
-            vals_out[pos] = vals_in[i];
+            s_keys[pos] = key[k];
+            s_vals[pos] = vals_in[i];
         }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tile_n; i += RADIX_THREADS) {
+        const uint32_t kk = s_keys[i];
+        const uint32_t g = s_gbase[(kk >> shift) & mask] + i;
+        keys_out[g] = kk;
+        vals_out[g] = s_vals[i];
     }
 }
 } // namespace
@@ -196,7 +234,8 @@ int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, bool write
 
 int radix_num_passes(int nbits) { return nbits <= 0 ? 0 : (nbits + 7) / 8; }
 
-int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* hist, size_t hist_words, cudaStream_t s)
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* hist, size_t hist_words, cudaStream_t s,
+                     const uint32_t* n_dev)
 {
     const int passes = radix_num_passes(nbits);
     if (n == 0 || passes == 0) return 0;
@@ -214,10 +253,11 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits
     for (int p = 0; p < passes; p++) {
         const int shift = p * digit_bits;
         const uint32_t mask = bins - 1;
-        radix_hist_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], n, shift, mask, nb, hist); count_launches(1);
+        radix_hist_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], n, n_dev, shift, mask, nb, hist); count_launches(1);
         int rc = exclusive_scan_u32(hist, hist, (uint32_t)hwords, false, partials, s);
         if (rc) return rc;
-        radix_scatter_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, mask, nb, hist); count_launches(1);
+        radix_scatter_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, n_dev, shift, mask, nb, hist);
+        count_launches(1);
         cur ^= 1;
     }
     return cur;

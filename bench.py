@@ -51,7 +51,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -190,6 +190,11 @@ def main():
 
     if not have_gpu:
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    # clocks are sampled for the whole run; starting nvidia-smi here keeps its (slow, driver-locking) start-up out of the
+    # timed regions
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get("GSR_BENCH_NO_SAMPLER"):
+        sampler.start()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     pkg = load_ours()  # also provides GaussianRasterizationSettings for the reference arm
@@ -244,18 +249,36 @@ def main():
         allreduce_grads()
 
     loss_host = [0.0]
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def stage_view(v):
+        """H2D of view v's inputs (camera + ground truth) from pinned memory on the copy stream, double-buffered like a
+        prefetching data loader; the compute stream waits on the event before using them."""
+        with torch.cuda.stream(copy_stream):
+            cam = wl["cams"][v]
+            mats = [cam[k + "_pin"].to(device, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos")]
+            gi = gt_img[v].to(device, non_blocking=True)
+            gd = gt_dep[v].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return mats, gi, gd, ev
+
+    pending = {}
 
     def step_e2e():
         zero_grads()
         total = None
         for v in range(V):
             cam = wl["cams"][v]
-            cam["viewmatrix_dev"].copy_(cam["viewmatrix_pin"], non_blocking=True)
-            cam["projmatrix_dev"].copy_(cam["projmatrix_pin"], non_blocking=True)
-            cam["campos_dev"].copy_(cam["campos_pin"], non_blocking=True)
-            gi = gt_img[v].to(device, non_blocking=True)
-            gd = gt_dep[v].to(device, non_blocking=True)
-            rs = settings_for(pkg, cam, bg, device)
+            if v not in pending:
+                pending[v] = stage_view(v)
+            mats, gi, gd, ev = pending.pop(v)
+            torch.cuda.current_stream().wait_event(ev)
+            for t in mats + [gi, gd]:
+                t.record_stream(torch.cuda.current_stream())
+            nv = (v + 1) % V
+            pending[nv] = stage_view(nv)  # next view's (next step's) inputs travel while this view computes
+            rs = settings_for(pkg, dict(cam, viewmatrix_dev=mats[0], projmatrix_dev=mats[1], campos_dev=mats[2]), bg, device)
             means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
             color, radii, depth, alpha, segment = rasterize(leaves, means2D, rs)
             dn = depth / (depth.max() + 1e-5)  # gaussian_renderer/__init__.py:375
@@ -265,22 +288,34 @@ def main():
         allreduce_grads()
         loss_host[0] = float(total.item())  # D2H read of the step's result
 
+    step_stats = {}
+
     def timed(fn, steps, warmup):
+        import gc
+
         for _ in range(warmup + args.extra_warmup):
             fn()
+        # a full (generation-2) Python GC pass walks every object torch/numpy created at import time (30-40 ms, seen as a
+        # single slow step); collect now and freeze the survivors so no such pass can land inside the timed region
+        gc.collect()
+        gc.freeze()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         t0 = time.time()
-        e0.record()
-        for _ in range(steps):
+        evs[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
         t1 = time.time()
-        ms = e0.elapsed_time(e1)
+        ms = evs[0].elapsed_time(evs[steps])  # the K steps, bracketed
+        if os.environ.get("GSR_BENCH_DEBUG_STEPS"):
+            print("STEPS", fn.__name__, [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(steps)], file=sys.stderr, flush=True)
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        step_stats[fn.__name__] = {"median_ms": round(per[len(per) // 2], 4), "min_ms": round(per[0], 4), "max_ms": round(per[-1], 4)}
         if dist is not None:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,10 +336,6 @@ def main():
             print("DEBUG", name, "wall_ms=%.3f" % ((time.time() - t0) * 1e3), pkg._lib.stage_times(), file=sys.stderr, flush=True)
         Ld.gsr_set_profiling(0)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     L = pkg._lib.lib()
     launches0 = int(L.gsr_launch_count())
     ms_dev, t0, t1 = timed(step_device, args.steps, args.warmup)
@@ -412,6 +443,7 @@ def main():
         "roofline_step": {"alg_bytes": bytes_step, "achieved": round(bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9, 1), "peak": hbm_peak,
                           "unit": "GB/s", "frac": round(bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9 / hbm_peak, 4)},
         "cpu_baseline": cpu_baseline,
+        "step_ms": step_stats,
     }
     if stages is not None:
         line["stages"] = stages

@@ -85,6 +85,11 @@ class _Alloc:
         except Exception:  # report as allocation failure through the C ABI
             return 0
 
+    def release(self):
+        """Break the self -> CFUNCTYPE -> bound method -> self reference cycle and drop the buffer references."""
+        self.cb = None
+        self.bufs = None
+
 
 def _view_struct(rs, M, num_class, keep):
     bg = _prep(rs.bg, keep["device"], "bg")
@@ -137,10 +142,14 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
         alloc = _Alloc(device)
         R = ctypes.c_int32(0)
         stream = torch.cuda.current_stream(device).cuda_stream
-        rc = L.gsr_forward(ctypes.byref(view), ctypes.byref(gin), ctypes.byref(out), alloc.cb, None, ctypes.byref(R), stream)
+        try:
+            rc = L.gsr_forward(ctypes.byref(view), ctypes.byref(gin), ctypes.byref(out), alloc.cb, None, ctypes.byref(R), stream)
+            bufs = alloc.bufs
+        finally:
+            alloc.release()  # the ctypes callback <-> bound method cycle would otherwise pin ~1 GB of state until a GC pass
         _lib.check(rc, "gsr_forward")
         e = lambda t: t if t is not None else torch.empty(0, dtype=torch.uint8, device=device)
-        return R.value, color, depth, segment, alpha, radii, e(alloc.bufs[0]), e(alloc.bufs[1]), e(alloc.bufs[2])
+        return R.value, color, depth, segment, alpha, radii, e(bufs[0]), e(bufs[1]), e(bufs[2])
 
 
 def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotations, cov3Ds_precomp, grad_color, grad_segment, grad_depth,

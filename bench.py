@@ -160,10 +160,20 @@ def settings_for(pkg, cam, bg, device):
         viewmatrix=cam["viewmatrix_dev"], projmatrix=cam["projmatrix_dev"], sh_degree=3, campos=cam["campos_dev"], prefiltered=False, debug=False)
 
 
+def _claim_stdout():
+    """NCCL / torchrun print banners to fd 1; the contract is ONE JSON line on stdout. Park the real stdout on a private fd
+    and point fd 1 at stderr for the rest of the run."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
@@ -186,7 +196,7 @@ def main():
 
     syn = importlib.import_module(PKG + ".synthetic")
     if args.impl == "reference" and (not have_gpu or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C.so"))):
-        return reference_cpu_port(args, syn)
+        return reference_cpu_port(args, syn, out)
 
     if not have_gpu:
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
@@ -208,7 +218,7 @@ def main():
 
     rasterize = make_rasterize_fn(args.impl, pkg)
     if rasterize is None:
-        return reference_cpu_port(args, syn)
+        return reference_cpu_port(args, syn, out)
 
     V = args.views_per_rank
     wl = build_workload(pkg, syn, args.workload, device, V, rank * V)
@@ -304,18 +314,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ms0 = torch.cuda.memory_stats(device)
+        host_t = []
         t0 = time.time()
         evs[0].record()
         for i in range(steps):
+            h0 = time.perf_counter()
             fn()
+            host_t.append((time.perf_counter() - h0) * 1e3)
             evs[i + 1].record()
         torch.cuda.synchronize()
         t1 = time.time()
+        ms1 = torch.cuda.memory_stats(device)
         ms = evs[0].elapsed_time(evs[steps])  # the K steps, bracketed
         if os.environ.get("GSR_BENCH_DEBUG_STEPS"):
             print("STEPS", fn.__name__, [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(steps)], file=sys.stderr, flush=True)
         per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
-        step_stats[fn.__name__] = {"median_ms": round(per[len(per) // 2], 4), "min_ms": round(per[0], 4), "max_ms": round(per[-1], 4)}
+        step_stats[fn.__name__] = {"median_ms": round(per[len(per) // 2], 4), "min_ms": round(per[0], 4), "max_ms": round(per[-1], 4),
+                                   "host_max_ms": round(max(host_t), 3), "host_median_ms": round(sorted(host_t)[len(host_t) // 2], 3),
+                                   "cudaMalloc_calls": int(ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0)),
+                                   "cudaFree_calls": int(ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0))}
         if dist is not None:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -344,6 +362,20 @@ def main():
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
     if rank == 0:
         sampler.stop()
+
+    comm_ms = None
+    if dist is not None:
+        for _ in range(2):
+            allreduce_grads()
+        torch.cuda.synchronize()
+        dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            allreduce_grads()
+        c1.record()
+        torch.cuda.synchronize()
+        comm_ms = c0.elapsed_time(c1) / 5
 
     views_total = V * nranks * args.steps
     value = views_total / (ms_dev / 1e3)
@@ -445,11 +477,17 @@ def main():
         "cpu_baseline": cpu_baseline,
         "step_ms": step_stats,
     }
+    if comm_ms is not None:
+        gbytes = 61 * 4 * P / 1e9
+        line["collective"] = {"op": "6 x ncclAllReduce(sum, fp32)", "bytes": int(61 * 4 * P), "ms": round(comm_ms, 3),
+                              "algbw_GBps": round(gbytes / (comm_ms * 1e-3), 1),
+                              "busbw_GBps": round(gbytes / (comm_ms * 1e-3) * 2 * (nranks - 1) / nranks, 1)}
     if stages is not None:
         line["stages"] = stages
     if args.impl == "reference":
         line["impl"] = "reference"
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -512,14 +550,15 @@ def run_cpu_baseline(syn, workload, row_stride=17):
             "measured_s": round(t2 - t0, 2)}
 
 
-def reference_cpu_port(args, syn):
+def reference_cpu_port(args, syn, out):
     """Fallback of `--impl reference` when the reference CUDA build (oracle/_ref) or a GPU is unavailable: the C port."""
     cb = run_cpu_baseline(syn, args.workload)
     line = {"metric": "train-step it/s (fwd+bwd, 1080p, 6M gaussians)", "value": cb["value"], "unit": "it/s", "n_gpus": 0, "steps": 1, "warmup": 0,
             "ms_per_step": round(1e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": args.workload}, "impl": "reference", "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     return 0
 
 

@@ -44,7 +44,7 @@ class GsrPixelGrads(ctypes.Structure):
 class GsrParamGrads(ctypes.Structure):
     _fields_ = [("dL_dmeans3D", ctypes.c_void_p), ("dL_dmeans2D", ctypes.c_void_p), ("dL_dsh", ctypes.c_void_p), ("dL_dcolors", ctypes.c_void_p),
                 ("dL_dsegments", ctypes.c_void_p), ("dL_dopacity", ctypes.c_void_p), ("dL_dscales", ctypes.c_void_p),
-                ("dL_drotations", ctypes.c_void_p), ("dL_dcov3D", ctypes.c_void_p)]
+                ("dL_drotations", ctypes.c_void_p), ("dL_dcov3D", ctypes.c_void_p), ("accumulate", ctypes.c_int32)]
 
 
 class GsrStateExport(ctypes.Structure):

@@ -358,39 +358,56 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
             const int id_rr = __shfl_sync(0xffffffffu, idx, rr);
             float* dst = a.out.dL_dsh + (size_t)id_rr * row_floats;
             const float* src = &s_sh[warp][rr * SH_ROW_STRIDE];
-            for (int k = lane; k < row_floats; k += 32) dst[k] = src[k];
+            if (a.out.accumulate) {
+                for (int k = lane; k < row_floats; k += 32) dst[k] += src[k];
+            } else {
+                for (int k = lane; k < row_floats; k += 32) dst[k] = src[k];
+            }
         }
     }
     if (!visible) return;
 
     // ---- remaining gradient rows of this visible Gaussian (rows of invisible Gaussians were zero-filled beforehand) ----
     const size_t i = (size_t)idx;
+    const bool acc = a.out.accumulate != 0;
+    auto put = [acc](float* p, float v) {
+        if (acc) *p += v;
+        else *p = v;
+    };
     if (a.out.dL_dmeans3D) {
-        a.out.dL_dmeans3D[3 * i + 0] = dL_dmean.x;
-        a.out.dL_dmeans3D[3 * i + 1] = dL_dmean.y;
-        a.out.dL_dmeans3D[3 * i + 2] = dL_dmean.z;
+        put(a.out.dL_dmeans3D + 3 * i + 0, dL_dmean.x);
+        put(a.out.dL_dmeans3D + 3 * i + 1, dL_dmean.y);
+        put(a.out.dL_dmeans3D + 3 * i + 2, dL_dmean.z);
     }
     if (a.out.dL_dmeans2D) {
-        a.out.dL_dmeans2D[3 * i + 0] = dL_dmean2D.x;
-        a.out.dL_dmeans2D[3 * i + 1] = dL_dmean2D.y;
-        a.out.dL_dmeans2D[3 * i + 2] = 0.f;
+        put(a.out.dL_dmeans2D + 3 * i + 0, dL_dmean2D.x);
+        put(a.out.dL_dmeans2D + 3 * i + 1, dL_dmean2D.y);
+        if (!acc) a.out.dL_dmeans2D[3 * i + 2] = 0.f;
     }
-    if (a.out.dL_dopacity) a.out.dL_dopacity[i] = dL_dopacity;
+    if (a.out.dL_dopacity) put(a.out.dL_dopacity + i, dL_dopacity);
     if (a.out.dL_dcolors) {
-        a.out.dL_dcolors[3 * i + 0] = dL_dcolor.x;
-        a.out.dL_dcolors[3 * i + 1] = dL_dcolor.y;
-        a.out.dL_dcolors[3 * i + 2] = dL_dcolor.z;
+        put(a.out.dL_dcolors + 3 * i + 0, dL_dcolor.x);
+        put(a.out.dL_dcolors + 3 * i + 1, dL_dcolor.y);
+        put(a.out.dL_dcolors + 3 * i + 2, dL_dcolor.z);
     }
-    if (a.out.dL_dsegments && a.S == 2) *reinterpret_cast<float2*>(a.out.dL_dsegments + 2 * i) = dL_dseg;
+    if (a.out.dL_dsegments && a.S == 2) {
+        put(a.out.dL_dsegments + 2 * i + 0, dL_dseg.x);
+        put(a.out.dL_dsegments + 2 * i + 1, dL_dseg.y);
+    }
     if (a.out.dL_dscales) {
-        a.out.dL_dscales[3 * i + 0] = dL_dscale.x;
-        a.out.dL_dscales[3 * i + 1] = dL_dscale.y;
-        a.out.dL_dscales[3 * i + 2] = dL_dscale.z;
+        put(a.out.dL_dscales + 3 * i + 0, dL_dscale.x);
+        put(a.out.dL_dscales + 3 * i + 1, dL_dscale.y);
+        put(a.out.dL_dscales + 3 * i + 2, dL_dscale.z);
     }
-    if (a.out.dL_drotations) *reinterpret_cast<float4*>(a.out.dL_drotations + 4 * i) = dL_drot;
+    if (a.out.dL_drotations) {
+        put(a.out.dL_drotations + 4 * i + 0, dL_drot.x);
+        put(a.out.dL_drotations + 4 * i + 1, dL_drot.y);
+        put(a.out.dL_drotations + 4 * i + 2, dL_drot.z);
+        put(a.out.dL_drotations + 4 * i + 3, dL_drot.w);
+    }
     if (a.out.dL_dcov3D) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) a.out.dL_dcov3D[6 * i + k] = dL_dcov3D[k];
+        for (int k = 0; k < 6; k++) put(a.out.dL_dcov3D + 6 * i + k, dL_dcov3D[k]);
     }
 }
 
@@ -427,8 +444,9 @@ int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
         {a.out.dL_dsh, P * (size_t)a.M * 3}, {a.out.dL_dmeans3D, P * 3}, {a.out.dL_dmeans2D, P * 3}, {a.out.dL_dopacity, P},
         {a.out.dL_dcolors, P * 3}, {a.out.dL_dsegments, P * (size_t)(a.S > 0 ? a.S : 0)}, {a.out.dL_dscales, P * 3},
         {a.out.dL_drotations, P * 4}, {a.out.dL_dcov3D, P * 6}};
-    for (auto& f : fills)
-        if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
+    if (!a.out.accumulate)
+        for (auto& f : fills)
+            if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
     const uint32_t nb = (a.g.slots + BWD_THREADS - 1) / BWD_THREADS; // capacity: V is only known on the device here
     preprocess_bwd_kernel<<<nb, BWD_THREADS, 0, s>>>(a); count_launches(1);
     return 0;

@@ -153,9 +153,13 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
 
 
 def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotations, cov3Ds_precomp, grad_color, grad_segment, grad_depth,
-                     grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, needs=None):
+                     grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, needs=None, out=None, accumulate=False):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:127-221) over gsr_backward. Returns a dict of dense
-    gradients (zeros for invisible Gaussians). `needs` optionally names the gradients to produce."""
+    gradients (zeros for invisible Gaussians). `needs` optionally names the gradients to produce.
+
+    `out` (dict name -> preallocated contiguous fp32 tensor, e.g. views of one flat buffer) makes the kernels write there
+    instead of fresh tensors; with `accumulate=True` the rows of visible Gaussians are ADDED to `out` and nothing else is
+    touched (multi-view accumulation without a zero-fill or a torch add per view)."""
     L = _lib.lib()
     device = means3D.device
     P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
@@ -173,10 +177,17 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
         opts = dict(dtype=torch.float32, device=device)
         grads = {}
         for n in names:
-            if want[n] and have.get(n, True):
+            if out is not None:
+                t = out.get(n)
+                if t is not None and (tuple(t.shape) != shapes[n] or t.dtype != torch.float32 or not t.is_contiguous() or t.device != device):
+                    raise RuntimeError("out[%r] must be a contiguous float32 %s tensor on %s" % (n, shapes[n], device))
+                grads[n] = t if have.get(n, True) else None
+            elif want[n] and have.get(n, True):
                 grads[n] = torch.zeros(shapes[n], **opts) if P == 0 else torch.empty(shapes[n], **opts)
             else:
                 grads[n] = None
+        if accumulate and out is None:
+            raise RuntimeError("accumulate=True needs `out`")
         if P == 0:
             return grads
         keep = {"device": device}
@@ -195,7 +206,7 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
         pix = GsrPixelGrads(g_col.data_ptr(), _ptr(g_seg), _ptr(g_dep), _ptr(g_alp))
         pg = GsrParamGrads(_ptr(grads["means3D"]), _ptr(grads["means2D"]), _ptr(grads["sh"]), _ptr(grads["colors_precomp"]),
                            _ptr(grads["segments"]), _ptr(grads["opacities"]), _ptr(grads["scales"]), _ptr(grads["rotations"]),
-                           _ptr(grads["cov3Ds_precomp"]))
+                           _ptr(grads["cov3Ds_precomp"]), int(bool(accumulate)))
         state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
         nscratch = L.gsr_backward_scratch_bytes(P)
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)

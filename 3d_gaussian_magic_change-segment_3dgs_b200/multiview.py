@@ -76,3 +76,49 @@ def multiview_step(leaves, cams, render_fn, loss_fn, rank=0, world=1, dist=None,
         if stats is not None:
             stats.allreduce(dist, group)
     return total
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Flat gradient buffer + in-kernel accumulation (SURVEY.md 8e / 8f-1): the rasterizer's backward adds each view's
+# gradient rows straight into views of ONE flat fp32 buffer, which is then summed over ranks with a single NCCL all-reduce.
+# ---------------------------------------------------------------------------------------------------------------------
+class FlatGradients:
+    """[61 * P] fp32 buffer, tensor-major: means3D | shs | segments | opacities | scales | rotations. `views[name]` are
+    contiguous views shaped like the rasterizer inputs; they can be installed as the `.grad` of the leaves."""
+
+    def __init__(self, P, device, sh_coeffs=16, num_class=2):
+        self.shapes = {"means3D": (P, 3), "shs": (P, sh_coeffs, 3), "segments": (P, num_class), "opacities": (P, 1), "scales": (P, 3),
+                       "rotations": (P, 4)}
+        n = sum(int(torch.Size(s).numel()) for s in self.shapes.values())
+        self.buffer = torch.zeros(n, dtype=torch.float32, device=device)
+        self.views, off = {}, 0
+        for name, shape in self.shapes.items():
+            cnt = int(torch.Size(shape).numel())
+            self.views[name] = self.buffer[off:off + cnt].view(shape)
+            off += cnt
+
+    def backward_out(self, means2D_grad=None):
+        """dict for `_backward_native(out=...)` (the native names differ from the leaf names for SH)."""
+        v = self.views
+        return {"means3D": v["means3D"], "means2D": means2D_grad, "sh": v["shs"], "colors_precomp": None, "segments": v["segments"],
+                "opacities": v["opacities"], "scales": v["scales"], "rotations": v["rotations"], "cov3Ds_precomp": None}
+
+    def install(self, leaves):
+        for name, t in leaves.items():
+            t.grad = self.views[name]
+
+    def allreduce(self, dist, group=None):
+        dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
+
+
+def native_view_backward(D, leaves, rs, fwd, upstream, flat, first, means2D_grad=None):
+    """Backward of one view into the flat buffer: overwrite (zero-fill + visible rows) for the step's first local view,
+    accumulate (visible rows only) for the following ones. `D` is the drop-in diff_gaussian_rasterization module, `fwd`
+    the 9-tuple returned by D._forward_native, `upstream` a dict with dL/d{color, depth, alpha, segment} (missing = zeros)."""
+    R, color, depth, segment, alpha, radii, geom, binb, img = fwd
+    e = torch.empty(0)
+    if means2D_grad is not None and not first:
+        means2D_grad.zero_()  # per-view screen-space gradient (densification statistics need each view's own norm)
+    return D._backward_native(rs, leaves["means3D"], radii, e, leaves["segments"], leaves["scales"], leaves["rotations"], e,
+                              upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"), leaves["shs"],
+                              geom, R, binb, img, alpha, out=flat.backward_out(means2D_grad), accumulate=not first)

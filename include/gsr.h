@@ -101,7 +101,10 @@ typedef struct GsrPixelGrads {
     const float* dL_dalpha;   /* [1,H,W] or NULL (= zeros) */
 } GsrPixelGrads;
 
-/* Dense gradients, every row written (zeros for invisible Gaussians). NULL members are skipped. */
+/* Dense gradients. accumulate == 0: every row is written (zeros for invisible Gaussians). accumulate != 0: the rows of
+ * visible Gaussians are ADDED to what the buffers hold and nothing else is touched -- the multi-view path, where several
+ * views of one step sum into one flat gradient buffer without a dense zero-fill or a torch add per view.
+ * NULL members are skipped. */
 typedef struct GsrParamGrads {
     float* dL_dmeans3D;   /* [P,3] */
     float* dL_dmeans2D;   /* [P,3] (third column 0) */
@@ -112,6 +115,7 @@ typedef struct GsrParamGrads {
     float* dL_dscales;    /* [P,3] (needs scales) */
     float* dL_drotations; /* [P,4] (needs rotations) */
     float* dL_dcov3D;     /* [P,6] */
+    int32_t accumulate;
 } GsrParamGrads;
 
 int gsr_abi_version(void);

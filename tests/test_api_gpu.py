@@ -131,3 +131,39 @@ def test_tile_lists_are_sorted_partition_full_size():
     assert bool((out["radii"][st["point_list"].long()] > 0).all())
     assert bool((st["n_contrib"].view(840, 1297).long() <= (rng[:, 1] - rng[:, 0]).max()).all())
     assert torch.isfinite(out["color"]).all() and float(out["alpha"].max()) <= 1.0 + 1e-4
+
+
+def test_accumulate_mode_sums_views_into_flat_buffer():
+    """gsr_backward(accumulate): two views accumulated into one flat buffer == sum of the two dense gradients; untouched rows
+    keep what the first (overwrite) view wrote; densification inputs stay per view."""
+    import importlib
+
+    Pk = H.pkg()
+    mv = importlib.import_module(H.PKG_NAME + ".multiview")
+    D = Pk.diff_gaussian_rasterization
+    syn = H.synthetic()
+    P, W, Hh = 30_000, 320, 240
+    gs, cam0 = syn.make_scene(P, W, Hh, seed=61, yaw_deg=0.0)
+    cam1 = syn.make_camera(W, Hh, yaw_deg=45.0)
+    gs = H.to_dev(gs)
+    ug = H.to_dev(syn.upstream_grads(W, Hh, 61, with_depth=True, with_segment=True, with_alpha=True))
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    flat = mv.FlatGradients(P, "cuda")
+    flat.buffer.fill_(123.0)  # stale content must be overwritten by the first view
+    e = torch.empty(0)
+    dense = []
+    for vi, cam in enumerate([cam0, cam1]):
+        rs = H.settings(cam, bg)
+        fwd = D._forward_native(gs["means3D"], gs["shs"], e, gs["segments"], gs["opacities"], gs["scales"], gs["rotations"], e, rs)
+        m2 = torch.zeros(P, 3, device="cuda")
+        mv.native_view_backward(D, gs, rs, fwd, ug, flat, first=(vi == 0), means2D_grad=m2)
+        R, color, depth, segment, alpha, radii, geom, binb, img = fwd
+        g = D._backward_native(rs, gs["means3D"], radii, e, gs["segments"], gs["scales"], gs["rotations"], e, ug["color"], ug["segment"],
+                               ug["depth"], ug["alpha"], gs["shs"], geom, R, binb, img, alpha)
+        dense.append(g)
+        assert H.rel_linf(m2, g["means2D"]) <= 1e-6
+    names = {"means3D": "means3D", "shs": "sh", "segments": "segments", "opacities": "opacities", "scales": "scales", "rotations": "rotations"}
+    for leaf, nat in names.items():
+        exp = dense[0][nat] + dense[1][nat]
+        assert H.rel_linf(flat.views[leaf], exp) <= 1e-6, leaf
+    assert flat.buffer.numel() == 61 * P

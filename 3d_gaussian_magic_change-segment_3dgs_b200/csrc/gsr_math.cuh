@@ -55,30 +55,6 @@ __device__ __forceinline__ M3 m3_transpose(const M3& a)
 }
 
 // Camera matrices are 16 floats indexed column-major (the reference passes the transposed row-major matrix).
-struct Cam
-{
-    float v[16]; // view
-    float p[16]; // full projection
-    float cx, cy, cz;
-};
-
-__device__ __forceinline__ void load_cam(Cam& c, const float* __restrict__ view, const float* __restrict__ proj,
-                                         const float* __restrict__ campos)
-{
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        c.v[i] = __ldg(view + i);
-        c.p[i] = __ldg(proj + i);
-    }
-    if (campos) {
-        c.cx = __ldg(campos);
-        c.cy = __ldg(campos + 1);
-        c.cz = __ldg(campos + 2);
-    } else {
-        c.cx = c.cy = c.cz = 0.f;
-    }
-}
-
 __device__ __forceinline__ float3 xform_point(const float3& p, const float* m) // transformPoint4x3
 {
     float3 t = {

@@ -102,6 +102,8 @@ static HostSync* host_sync()
     return &h;
 }
 
+static thread_local uint32_t g_last_visible = 0;
+
 static int ceil_log2(uint32_t v)
 {
     int b = 0;
@@ -251,6 +253,7 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
         return GSR_ERR_PREFILTERED;
     }
     const uint32_t V = counters[CNT_VISIBLE];
+    g_last_visible = V;
     const unsigned long long R64 = (unsigned long long)counters[CNT_RENDERED_LO] | ((unsigned long long)counters[CNT_RENDERED_LO + 1] << 32);
     if (R64 > 0x7fffffffull) {
         set_error("%llu tile instances exceed the int32 limit", R64);
@@ -318,10 +321,57 @@ extern "C" size_t gsr_backward_scratch_bytes(int32_t P)
     return nblk * PRE_BLOCK * GRAD_REC_FLOATS * sizeof(float) + 256;
 }
 
+static int backward_impl(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
+                         const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, cudaStream_t s,
+                         uint32_t* packets, uint32_t capacity, uint32_t* count_dev);
+
 extern "C" int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                             const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, gsr_stream_t stream_)
 {
-    cudaStream_t s = (cudaStream_t)stream_;
+    return backward_impl(view, in, radii, state, alpha, pix, grads, scratch, scratch_bytes, (cudaStream_t)stream_, nullptr, 0, nullptr);
+}
+
+extern "C" uint32_t gsr_last_num_visible(void) { return g_last_visible; }
+
+extern "C" int gsr_backward_packets(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
+                                    const GsrPixelGrads* pix, uint32_t* packets, uint32_t capacity, uint32_t* count_dev, float* dL_dmeans2D,
+                                    void* scratch, size_t scratch_bytes, gsr_stream_t stream_)
+{
+    if (!packets || !count_dev) {
+        set_error("gsr_backward_packets: packets/count_dev missing");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (in && in->P > 0 && (!in->shs || !in->scales || !in->rotations)) {
+        set_error("gsr_backward_packets needs shs and scales/rotations");
+        return GSR_ERR_UNSUPPORTED;
+    }
+    GsrParamGrads g;
+    memset(&g, 0, sizeof(g));
+    g.dL_dmeans2D = dL_dmeans2D;
+    return backward_impl(view, in, radii, state, alpha, pix, &g, scratch, scratch_bytes, (cudaStream_t)stream_, packets, capacity, count_dev);
+}
+
+extern "C" int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, const float* campos,
+                                 const uint32_t* packets, uint32_t capacity, const uint32_t* count_dev, const GsrParamGrads* grads,
+                                 gsr_stream_t stream_)
+{
+    if (P <= 0 || capacity == 0) return 0;
+    if (!means3D || !campos || !packets || !count_dev || !grads || sh_coeffs > 16 || sh_degree < 0 || sh_degree > 3) {
+        set_error("gsr_apply_packets: invalid argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    ApplyPacketsArgs a;
+    a.P = P; a.D = sh_degree; a.M = sh_coeffs; a.S = num_class; a.means3D = means3D; a.campos = campos;
+    a.packets = packets; a.capacity = capacity; a.count = count_dev; a.out = *grads;
+    launch_apply_packets(a, (cudaStream_t)stream_);
+    GSR_LAUNCHED((cudaStream_t)stream_, false, "apply_packets");
+    return 0;
+}
+
+static int backward_impl(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
+                         const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, cudaStream_t s,
+                         uint32_t* packets, uint32_t capacity, uint32_t* count_dev)
+{
     int rc = validate(view, in);
     if (rc) return rc;
     if (in->P == 0) return 0;
@@ -371,6 +421,7 @@ extern "C" int gsr_backward(const GsrView* view, const GsrGaussians* in, const i
     pb.focal_x = W / (2.0f * view->tanfovx);
     pb.radii = radii; pb.g = g; pb.grad_rec = grad_rec; pb.out = *grads;
     pb.colors_precomp_given = in->colors_precomp != nullptr;
+    pb.packets = packets; pb.packet_capacity = capacity; pb.packet_count = count_dev;
     if (!in->shs) pb.out.dL_dsh = nullptr;
     if (!in->scales) { pb.out.dL_dscales = nullptr; pb.out.dL_drotations = nullptr; }
     launch_preprocess_bwd(pb, s);

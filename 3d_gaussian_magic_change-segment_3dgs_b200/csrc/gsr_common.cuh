@@ -185,7 +185,23 @@ struct PreBwdArgs
     const float* grad_rec; // [slots][12]
     GsrParamGrads out;
     bool colors_precomp_given;
+    // packet mode (multi-GPU gradient exchange): one GSR_PACKET_WORDS record per visible Gaussian instead of dense rows
+    uint32_t* packets;
+    uint32_t packet_capacity;
+    uint32_t* packet_count;
 };
+
+struct ApplyPacketsArgs
+{
+    int P, D, M, S;
+    const float* means3D;
+    const float* campos;
+    const uint32_t* packets;
+    uint32_t capacity;
+    const uint32_t* count;
+    GsrParamGrads out;
+};
+int launch_apply_packets(const ApplyPacketsArgs& a, cudaStream_t s);
 
 struct RenderArgs
 {

@@ -314,6 +314,39 @@ __device__ __forceinline__ float3 sh_backward(int deg, const float3& pos, const 
     return dnormvdv(float3{dir_orig.x, dir_orig.y, dir_orig.z}, dL_ddir);
 }
 
+// The scalars dRGB/dsh_k that multiply dL_dRGB in sh_backward, for a unit direction (x,y,z); 0 above the active degree.
+// Same expressions as sh_backward, so (sh_basis[k] * dL_dRGB) reproduces its dL_dsh rows bit for bit. Used by the
+// receiving side of the multi-GPU gradient exchange, which rebuilds the 48-float SH row from the 3-float colour gradient.
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* w)
+{
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = 0.f;
+    w[0] = kSH0;
+    if (deg > 0) {
+        w[1] = -kSH1 * y;
+        w[2] = kSH1 * z;
+        w[3] = -kSH1 * x;
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z;
+            float xy = x * y, yz = y * z, xz = x * z;
+            w[4] = kSH2[0] * xy;
+            w[5] = kSH2[1] * yz;
+            w[6] = kSH2[2] * (2.f * zz - xx - yy);
+            w[7] = kSH2[3] * xz;
+            w[8] = kSH2[4] * (xx - yy);
+            if (deg > 2) {
+                w[9] = kSH3[0] * y * (3.f * xx - yy);
+                w[10] = kSH3[1] * xy * z;
+                w[11] = kSH3[2] * y * (4.f * zz - xx - yy);
+                w[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                w[13] = kSH3[4] * x * (4.f * zz - xx - yy);
+                w[14] = kSH3[5] * z * (xx - yy);
+                w[15] = kSH3[6] * x * (xx - 3.f * yy);
+            }
+        }
+    }
+}
+
 // Backward of cov3d_from_scale_rot (backward.cu:278-341): gradients w.r.t. the scale and the raw quaternion.
 __device__ __forceinline__ void cov3d_backward(const float3 scale, float mod, const float4 rot, const float* dL_dcov3D,
                                                float3& dL_dscale, float4& dL_drot)

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
         if (a.shs != nullptr) {
             const float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
             const unsigned cb = a.g.clamped[slot];
-            V3* sh_row = a.out.dL_dsh ? reinterpret_cast<V3*>(my_sh) : nullptr;
+            V3* sh_row = (a.out.dL_dsh && !a.packets) ? reinterpret_cast<V3*>(my_sh) : nullptr;
             const float3 d3 = sh_backward(a.D, mean, campos, reinterpret_cast<const V3*>(a.shs) + (size_t)idx * a.M, cb,
                                           V3{dL_dcolor.x, dL_dcolor.y, dL_dcolor.z}, ShRowWriter{sh_row});
             if (sh_row) // coefficients above the active degree get no gradient
@@ -350,6 +350,33 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
 
     // ---- SH gradient rows: each 192-B row leaves the warp as whole 128-B + 64-B bursts (a per-thread row write would
     //      touch 32 different rows per store instruction, half a sector each) ----
+    if (a.packets) {
+        // ---- packet mode: 17 words per visible Gaussian; the receiver rebuilds the SH rows from the colour gradient ----
+        if (r == 0) *a.packet_count = V;
+        if (visible && r < a.packet_capacity) {
+            float3 dRGB = dL_dcolor;
+            if (a.shs != nullptr) { // the clamp mask of sh_backward (backward.cu:31-34)
+                const unsigned cb = a.g.clamped[slot];
+                dRGB.x *= (cb & 1u) ? 0 : 1;
+                dRGB.y *= (cb & 2u) ? 0 : 1;
+                dRGB.z *= (cb & 4u) ? 0 : 1;
+            }
+            uint32_t* pk = a.packets + (size_t)r * GSR_PACKET_WORDS;
+            pk[0] = (uint32_t)idx;
+            float* pf = reinterpret_cast<float*>(pk);
+            pf[1] = dRGB.x; pf[2] = dRGB.y; pf[3] = dRGB.z;
+            pf[4] = dL_dmean.x; pf[5] = dL_dmean.y; pf[6] = dL_dmean.z;
+            pf[7] = dL_dopacity;
+            pf[8] = dL_dseg.x; pf[9] = dL_dseg.y;
+            pf[10] = dL_dscale.x; pf[11] = dL_dscale.y; pf[12] = dL_dscale.z;
+            pf[13] = dL_drot.x; pf[14] = dL_drot.y; pf[15] = dL_drot.z; pf[16] = dL_drot.w;
+            if (a.out.dL_dmeans2D) { // per-view screen-space gradient for the densification statistics (dense, pre-zeroed)
+                a.out.dL_dmeans2D[3 * (size_t)idx + 0] = dL_dmean2D.x;
+                a.out.dL_dmeans2D[3 * (size_t)idx + 1] = dL_dmean2D.y;
+            }
+        }
+        return;
+    }
     if (a.out.dL_dsh) {
         __syncwarp();
         const int row_floats = a.M * 3;
@@ -411,6 +438,77 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
     }
 }
 
+// Receiving side of the multi-GPU gradient exchange: ADD one view's packets into dense gradient rows. A warp owns 32
+// packets; the 192-B SH rows are rebuilt as basis(dir) x dL_dRGB and added row-cooperatively (coalesced bursts).
+constexpr int APPLY_THREADS = 128;
+__global__ void __launch_bounds__(APPLY_THREADS) apply_packets_kernel(const ApplyPacketsArgs a)
+{
+    __shared__ float s_w[APPLY_THREADS / 32][32][20]; // per packet: 16 basis weights + dRGB
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * APPLY_THREADS + threadIdx.x;
+    const uint32_t n = min(*a.count, a.capacity);
+    if ((r & ~31u) >= n) return;
+    const bool valid = r < n;
+    uint32_t id = 0;
+    float f[GSR_PACKET_WORDS];
+#pragma unroll
+    for (int k = 0; k < GSR_PACKET_WORDS; k++) f[k] = 0.f;
+    if (valid) {
+        const uint32_t* pk = a.packets + (size_t)r * GSR_PACKET_WORDS;
+        id = pk[0];
+#pragma unroll
+        for (int k = 1; k < GSR_PACKET_WORDS; k++) f[k] = __uint_as_float(pk[k]);
+    }
+    const size_t i = (size_t)id;
+    if (a.out.dL_dsh && a.M > 0) {
+        float w[16];
+        if (valid) {
+            const float3 pos = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
+            V3 dir_orig = {pos.x - a.campos[0], pos.y - a.campos[1], pos.z - a.campos[2]};
+            const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+            sh_basis(a.D, dir_orig.x / len, dir_orig.y / len, dir_orig.z / len, w);
+#pragma unroll
+            for (int k = 0; k < 16; k++) s_w[warp][lane][k] = w[k];
+            s_w[warp][lane][16] = f[1];
+            s_w[warp][lane][17] = f[2];
+            s_w[warp][lane][18] = f[3];
+        }
+        __syncwarp();
+        const uint32_t nrows = min(32u, n - (r & ~31u));
+        const int row_floats = a.M * 3;
+        for (uint32_t rr = 0; rr < nrows; rr++) {
+            const uint32_t id_rr = __shfl_sync(0xffffffffu, id, rr);
+            float* dst = a.out.dL_dsh + (size_t)id_rr * row_floats;
+            for (int k = lane; k < row_floats; k += 32) {
+                const int coef = k / 3, ch = k - 3 * coef;
+                if (coef < 16) dst[k] += s_w[warp][rr][coef] * s_w[warp][rr][16 + ch];
+            }
+        }
+    }
+    if (!valid) return;
+    if (a.out.dL_dmeans3D) {
+        a.out.dL_dmeans3D[3 * i + 0] += f[4];
+        a.out.dL_dmeans3D[3 * i + 1] += f[5];
+        a.out.dL_dmeans3D[3 * i + 2] += f[6];
+    }
+    if (a.out.dL_dopacity) a.out.dL_dopacity[i] += f[7];
+    if (a.out.dL_dsegments && a.S == 2) {
+        a.out.dL_dsegments[2 * i + 0] += f[8];
+        a.out.dL_dsegments[2 * i + 1] += f[9];
+    }
+    if (a.out.dL_dscales) {
+        a.out.dL_dscales[3 * i + 0] += f[10];
+        a.out.dL_dscales[3 * i + 1] += f[11];
+        a.out.dL_dscales[3 * i + 2] += f[12];
+    }
+    if (a.out.dL_drotations) {
+        a.out.dL_drotations[4 * i + 0] += f[13];
+        a.out.dL_drotations[4 * i + 1] += f[14];
+        a.out.dL_drotations[4 * i + 2] += f[15];
+        a.out.dL_drotations[4 * i + 3] += f[16];
+    }
+}
+
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
                                                            uint8_t* __restrict__ present)
 {
@@ -444,11 +542,20 @@ int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
         {a.out.dL_dsh, P * (size_t)a.M * 3}, {a.out.dL_dmeans3D, P * 3}, {a.out.dL_dmeans2D, P * 3}, {a.out.dL_dopacity, P},
         {a.out.dL_dcolors, P * 3}, {a.out.dL_dsegments, P * (size_t)(a.S > 0 ? a.S : 0)}, {a.out.dL_dscales, P * 3},
         {a.out.dL_drotations, P * 4}, {a.out.dL_dcov3D, P * 6}};
-    if (!a.out.accumulate)
+    if (a.packets) {
+        if (a.out.dL_dmeans2D) GSR_CUDA(cudaMemsetAsync(a.out.dL_dmeans2D, 0, P * 3 * sizeof(float), s));
+    } else if (!a.out.accumulate) {
         for (auto& f : fills)
             if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
+    }
     const uint32_t nb = (a.g.slots + BWD_THREADS - 1) / BWD_THREADS; // capacity: V is only known on the device here
     preprocess_bwd_kernel<<<nb, BWD_THREADS, 0, s>>>(a); count_launches(1);
+    return 0;
+}
+int launch_apply_packets(const ApplyPacketsArgs& a, cudaStream_t s)
+{
+    if (a.capacity == 0) return 0;
+    apply_packets_kernel<<<(a.capacity + APPLY_THREADS - 1) / APPLY_THREADS, APPLY_THREADS, 0, s>>>(a); count_launches(1);
     return 0;
 }
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s)

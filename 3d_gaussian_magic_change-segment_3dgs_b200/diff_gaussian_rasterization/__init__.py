@@ -219,6 +219,62 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
         return grads
 
 
+def last_num_visible():
+    """Visible Gaussians of the most recent forward on this thread (host value; the forward already synchronised for it)."""
+    return int(_lib.lib().gsr_last_num_visible())
+
+
+def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, grad_color, grad_segment, grad_depth, grad_alpha, sh,
+                             geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None):
+    """gsr_backward_packets: the backward of one view as compact per-visible-Gaussian packets (17 words each, see
+    include/gsr.h) instead of dense gradient rows. Returns (packets int32[capacity, 17], count int32[1])."""
+    L = _lib.lib()
+    device = means3D.device
+    P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
+    M = sh.size(1)
+    num_class = segments.size(1) if (segments is not None and segments.numel() > 0) else NUM_CLASS
+    with torch.cuda.device(device):
+        opts = dict(dtype=torch.float32, device=device)
+        keep = {"device": device}
+        view = _view_struct(rs, M, num_class, keep)
+        t_means, t_sh, t_seg = _prep(means3D, device, "means3D"), _prep(sh, device, "sh"), _prep(segments, device, "segments")
+        t_sc, t_rot = _prep(scales, device, "scales"), _prep(rotations, device, "rotations")
+        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), None, _ptr(t_seg), t_means.data_ptr(), _ptr(t_sc), _ptr(t_rot), None)
+        g_col = _prep(grad_color, device, "grad_color")
+        if g_col is None:
+            g_col = torch.zeros((NUM_CHANNELS, H, W), **opts)
+        g_seg, g_dep, g_alp = _prep(grad_segment, device, "grad_segment"), _prep(grad_depth, device, "grad_depth"), _prep(grad_alpha, device, "grad_alpha")
+        pix = GsrPixelGrads(g_col.data_ptr(), _ptr(g_seg), _ptr(g_dep), _ptr(g_alp))
+        state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
+        nscratch = L.gsr_backward_scratch_bytes(P)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
+        cap = max(int(capacity), 1)
+        packets = torch.empty((cap, _lib.GSR_PACKET_WORDS), dtype=torch.int32, device=device)
+        count = torch.zeros(1, dtype=torch.int32, device=device)
+        t_radii, t_alpha = radii.contiguous(), _prep(alpha, device, "alpha")
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = L.gsr_backward_packets(ctypes.byref(view), ctypes.byref(gin), t_radii.data_ptr(), ctypes.byref(state), t_alpha.data_ptr(),
+                                    ctypes.byref(pix), packets.data_ptr(), cap, count.data_ptr(), _ptr(means2D_grad), scratch.data_ptr(),
+                                    nscratch, stream)
+        _lib.check(rc, "gsr_backward_packets")
+        return packets, count
+
+
+def apply_packets(means3D, campos, sh_degree, sh_coeffs, packets, count, out, num_class=NUM_CLASS):
+    """gsr_apply_packets: ADD one view's packets into the dense gradient tensors of `out` (dict with the native names
+    means3D / sh / segments / opacities / scales / rotations; missing or None entries are skipped)."""
+    L = _lib.lib()
+    device = means3D.device
+    P = means3D.size(0)
+    with torch.cuda.device(device):
+        g = lambda n: _ptr(out.get(n))
+        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 1)
+        cp = _prep(campos, device, "campos")
+        rc = L.gsr_apply_packets(P, int(sh_degree), int(sh_coeffs), int(num_class), means3D.data_ptr(), cp.data_ptr(), packets.data_ptr(),
+                                 int(packets.size(0)), count.data_ptr(), ctypes.byref(pg), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "gsr_apply_packets")
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings):

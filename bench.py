@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--views-per-rank", type=int, default=1)
+    ap.add_argument("--grad-exchange", default="packets", choices=["packets", "dense"],
+                    help="N>1: all-gather 68-B gradient packets of the visible Gaussians (default) or all-reduce the dense flat buffer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-profile", action="store_true")
     args = ap.parse_args()
@@ -243,8 +245,14 @@ def main():
         for v in leaves.values():
             v.grad = None
 
+    e2e_sets = []
+
     def allreduce_grads():
         if dist is None:
+            return
+        if use_packets and e2e_sets:
+            mv.exchange_packets(Dmod, dist, flat, leaves, e2e_sets, all_campos, 3, nranks)
+            e2e_sets.clear()
             return
         if flat is not None:
             flat.allreduce(dist)
@@ -258,15 +266,27 @@ def main():
     Dmod = pkg.diff_gaussian_rasterization
     empty = torch.empty(0)
 
+    use_packets = use_flat and dist is not None and args.grad_exchange == "packets"
+    all_campos = None
+    if use_packets:  # every rank knows every camera of the step
+        all_campos = [[syn.make_camera(W, Hh, yaw_deg=45.0 * (r * V + v))["campos"].to(device) for v in range(V)] for r in range(nranks)]
+
     def step_device_flat():
-        """multi-view / multi-GPU step: every view's backward adds into ONE flat gradient buffer, one NCCL all-reduce."""
+        """multi-view / multi-GPU step. dense: every view's backward adds into ONE flat gradient buffer, one NCCL all-reduce.
+        packets: every view's backward emits 68-B packets of its visible Gaussians, one NCCL all-gather, local rebuild + sum."""
+        sets = []
         for v in range(V):
             rs = settings_for(pkg, wl["cams"][v], bg, device)
             with torch.no_grad():
                 fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"], leaves["scales"],
                                            leaves["rotations"], empty, rs)
-                mv.native_view_backward(Dmod, leaves, rs, fwd, ug, flat, first=(v == 0))
-        if dist is not None:
+                if use_packets:
+                    sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug))
+                else:
+                    mv.native_view_backward(Dmod, leaves, rs, fwd, ug, flat, first=(v == 0))
+        if use_packets:
+            mv.exchange_packets(Dmod, dist, flat, leaves, sets, all_campos, 3, nranks)
+        elif dist is not None:
             flat.allreduce(dist)
 
     def step_device():
@@ -320,7 +340,11 @@ def main():
                 loss = (color - gi).abs().mean() + 0.1 * (dn - gd).abs().mean()
                 loss.backward()  # pixel gradients only; the rasterizer backward runs natively into the flat buffer
                 with torch.no_grad():
-                    mv.native_view_backward(Dmod, leaves, rs, fwd, {"color": color.grad, "depth": depth.grad}, flat, first=(v == 0))
+                    pg = {"color": color.grad, "depth": depth.grad}
+                    if use_packets:
+                        e2e_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, pg))
+                    else:
+                        mv.native_view_backward(Dmod, leaves, rs, fwd, pg, flat, first=(v == 0))
             else:
                 means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
                 color, radii, depth, alpha, segment = rasterize(leaves, means2D, rs)
@@ -398,14 +422,27 @@ def main():
 
     comm_ms = None
     if dist is not None:
+        def comm_only():
+            if use_packets:
+                mv.exchange_packets(Dmod, dist, flat, leaves, comm_sets, all_campos, 3, nranks)
+            else:
+                flat.allreduce(dist)
+        comm_sets = []
+        if use_packets:
+            with torch.no_grad():
+                for v in range(V):
+                    rs = settings_for(pkg, wl["cams"][v], bg, device)
+                    fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"],
+                                               leaves["scales"], leaves["rotations"], empty, rs)
+                    comm_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug))
         for _ in range(2):
-            allreduce_grads()
+            comm_only()
         torch.cuda.synchronize()
         dist.barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for _ in range(5):
-            allreduce_grads()
+            comm_only()
         c1.record()
         torch.cuda.synchronize()
         comm_ms = c0.elapsed_time(c1) / 5
@@ -497,8 +534,11 @@ def main():
         "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d Gaussians SH3, %dx%d, rasterize_gaussians fwd (colour+depth+alpha+segment) + bwd (dL/dcolour, dL/ddepth), "
-                               "%d view(s)/rank/step%s" % (args.workload, P, W, Hh, V, ", gradients accumulated in one flat buffer (61 floats/Gaussian), "
-                                                           "one NCCL all-reduce" if nranks > 1 else ""),
+                               "%d view(s)/rank/step%s" % (args.workload, P, W, Hh, V,
+                                                           (", gradient exchange = NCCL all-gather of 68-B packets of the visible Gaussians + local "
+                                                            "rebuild into the flat buffer" if use_packets else
+                                                            ", gradients accumulated in one flat buffer (61 floats/Gaussian), one NCCL all-reduce")
+                                                           if nranks > 1 else ""),
                    "views_per_rank": V, "l2": "inputs (%.2f GB of parameters) are larger than the 126 MB L2" % (61 * 4 * P / 1e9), "stats": stats,
                    "alg_bytes_per_step": bytes_step},
         "e2e": {"value": round(e2e_value, 4), "unit": "it/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -513,9 +553,15 @@ def main():
     }
     if comm_ms is not None:
         gbytes = 61 * 4 * P / 1e9
-        line["collective"] = {"op": "1 x ncclAllReduce(sum, fp32) of the flat gradient buffer", "bytes": int(61 * 4 * P), "ms": round(comm_ms, 3),
-                              "algbw_GBps": round(gbytes / (comm_ms * 1e-3), 1),
-                              "busbw_GBps": round(gbytes / (comm_ms * 1e-3) * 2 * (nranks - 1) / nranks, 1)}
+        if use_packets:
+            line["collective"] = {"op": "ncclAllGather of gradient packets (68 B per visible Gaussian per view) + count all-gather + local "
+                                        "rebuild (memset + %d apply kernels)" % (nranks * V),
+                                  "bytes_sent_per_rank": int(68 * stats["V"] * V), "ms": round(comm_ms, 3),
+                                  "dense_allreduce_bytes": int(61 * 4 * P)}
+        else:
+            line["collective"] = {"op": "1 x ncclAllReduce(sum, fp32) of the flat gradient buffer", "bytes": int(61 * 4 * P),
+                                  "ms": round(comm_ms, 3), "algbw_GBps": round(gbytes / (comm_ms * 1e-3), 1),
+                                  "busbw_GBps": round(gbytes / (comm_ms * 1e-3) * 2 * (nranks - 1) / nranks, 1)}
     if stages is not None:
         line["stages"] = stages
     if args.impl == "reference":

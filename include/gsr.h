@@ -132,6 +132,26 @@ size_t gsr_backward_scratch_bytes(int32_t P);
 int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                  const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, gsr_stream_t stream);
 
+/* ---- multi-GPU gradient exchange (multi-view data parallelism) ----
+ * Instead of dense rows, the backward can emit one compact PACKET per visible Gaussian of the view:
+ *   word 0      Gaussian id (uint32)
+ *   words 1-3   dL/dRGB of the SH colour, clamp mask applied      words 4-6   dL/dmean3D (all paths, incl. the SH view direction)
+ *   word 7      dL/dopacity     words 8-9  dL/dsegment     words 10-12  dL/dscale     words 13-16  dL/drotation
+ * 68 B instead of the 244-B dense row: the 48-float SH gradient row is rank one, basis(view direction) x dL/dRGB, and is
+ * rebuilt by gsr_apply_packets on the receiving rank from the Gaussian's position and that view's camera centre.
+ * Packets are ordered by Gaussian id; *count_dev receives the number of visible Gaussians (packets beyond `capacity` are
+ * dropped -- size it with gsr_last_num_visible()). dL_dmeans2D (optional, dense [P,3]) is overwritten for the
+ * densification statistics. Requires shs + scales/rotations (the training configuration). */
+#define GSR_PACKET_WORDS 17
+int gsr_backward_packets(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
+                         const GsrPixelGrads* pix, uint32_t* packets, uint32_t capacity, uint32_t* count_dev, float* dL_dmeans2D,
+                         void* scratch, size_t scratch_bytes, gsr_stream_t stream);
+/* ADD the packets of one view (produced with camera centre `campos`, device [3]) into dense gradient rows. */
+int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, const float* campos,
+                      const uint32_t* packets, uint32_t capacity, const uint32_t* count_dev, const GsrParamGrads* grads, gsr_stream_t stream);
+/* Number of visible Gaussians of the most recent gsr_forward on the calling thread. */
+uint32_t gsr_last_num_visible(void);
+
 int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      gsr_stream_t stream);
 

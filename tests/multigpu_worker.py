@@ -1,0 +1,50 @@
+"""torchrun worker of tests/test_multigpu_gpu.py: N ranks, one view each; the packet exchange must equal the dense all-reduce
+of the per-rank dense gradients (<= 1e-6 relative) and leave bitwise-identical buffers on every rank."""
+import importlib
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # noqa: E402
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+Pk = H.pkg()
+mv = importlib.import_module(H.PKG_NAME + ".multiview")
+D = Pk.diff_gaussian_rasterization
+syn = H.synthetic()
+P, W, Hh = 60_000, 400, 304
+gs, _ = syn.make_scene(P, W, Hh, seed=81)
+gs = {k: v.to(dev) for k, v in gs.items()}
+cams = [syn.make_camera(W, Hh, yaw_deg=45.0 * r) for r in range(world)]
+ug = {k: (v.to(dev) if v is not None else None) for k, v in syn.upstream_grads(W, Hh, 81, with_depth=True, with_segment=True, with_alpha=True).items()}
+bg = torch.tensor([0.1, 0.2, 0.3])
+rs = H.settings(cams[rank], bg, device=dev)
+e = torch.empty(0)
+fwd = D._forward_native(gs["means3D"], gs["shs"], e, gs["segments"], gs["opacities"], gs["scales"], gs["rotations"], e, rs)
+# dense path: flat buffer + all-reduce
+dense = mv.FlatGradients(P, dev)
+mv.native_view_backward(D, gs, rs, fwd, ug, dense, first=True)
+dense.allreduce(dist)
+# packet path
+flat = mv.FlatGradients(P, dev)
+sets = [mv.native_view_backward_packets(D, gs, rs, fwd, ug)]
+campos = [[c["campos"].to(dev)] for c in cams]
+mv.exchange_packets(D, dist, flat, gs, sets, campos, 3, world)
+torch.cuda.synchronize()
+err = float((flat.buffer - dense.buffer).abs().max()) / float(dense.buffer.abs().max())
+assert err <= 1e-6, err
+# replicas bitwise identical
+ref = flat.buffer.clone()
+dist.broadcast(ref, 0)
+assert torch.equal(ref, flat.buffer), "replicas differ"
+if rank == 0:
+    print("multigpu ok: world=%d rel_err=%.3e" % (world, err))
+dist.destroy_process_group()

@@ -167,3 +167,44 @@ def test_accumulate_mode_sums_views_into_flat_buffer():
         exp = dense[0][nat] + dense[1][nat]
         assert H.rel_linf(flat.views[leaf], exp) <= 1e-6, leaf
     assert flat.buffer.numel() == 61 * P
+
+
+def test_gradient_packets_rebuild_dense_rows():
+    """gsr_backward_packets + gsr_apply_packets (the multi-GPU exchange format): applying a view's own packets to a zeroed flat
+    buffer reproduces the dense backward bit for bit (SH rows are rebuilt as basis(direction) x dL/dRGB); two views sum."""
+    import importlib
+
+    Pk = H.pkg()
+    mv = importlib.import_module(H.PKG_NAME + ".multiview")
+    D = Pk.diff_gaussian_rasterization
+    syn = H.synthetic()
+    P, W, Hh = 30_000, 320, 240
+    gs, cam0 = syn.make_scene(P, W, Hh, seed=71, yaw_deg=0.0)
+    cams = [cam0, syn.make_camera(W, Hh, yaw_deg=90.0)]
+    gs = H.to_dev(gs)
+    ug = H.to_dev(syn.upstream_grads(W, Hh, 71, with_depth=True, with_segment=True, with_alpha=True))
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    e = torch.empty(0)
+    flat = mv.FlatGradients(P, "cuda")
+    sets, dense, campos = [], [], []
+    for cam in cams:
+        rs = H.settings(cam, bg)
+        fwd = D._forward_native(gs["means3D"], gs["shs"], e, gs["segments"], gs["opacities"], gs["scales"], gs["rotations"], e, rs)
+        m2 = torch.zeros(P, 3, device="cuda")
+        sets.append(mv.native_view_backward_packets(D, gs, rs, fwd, ug, means2D_grad=m2))
+        R, color, depth, segment, alpha, radii, geom, binb, img = fwd
+        g = D._backward_native(rs, gs["means3D"], radii, e, gs["segments"], gs["scales"], gs["rotations"], e, ug["color"], ug["segment"],
+                               ug["depth"], ug["alpha"], gs["shs"], geom, R, binb, img, alpha)
+        dense.append(g)
+        campos.append(cam["campos"].cuda())
+        assert int(sets[-1][1]) == sets[-1][2] == int((radii > 0).sum())
+        assert torch.equal(m2, g["means2D"])
+    names = {"means3D": "means3D", "shs": "sh", "segments": "segments", "opacities": "opacities", "scales": "scales", "rotations": "rotations"}
+    # one view: bit-exact reconstruction
+    mv.exchange_packets(D, None, flat, gs, sets[:1], [campos[:1]], 3, world=1)
+    for leaf, nat in names.items():
+        assert torch.equal(flat.views[leaf], dense[0][nat]), leaf
+    # two views of one rank: the sum
+    mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1)
+    for leaf, nat in names.items():
+        assert H.rel_linf(flat.views[leaf], dense[0][nat] + dense[1][nat]) <= 1e-6, leaf

@@ -476,13 +476,33 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_packets_kernel(const Appl
         __syncwarp();
         const uint32_t nrows = min(32u, n - (r & ~31u));
         const int row_floats = a.M * 3;
-        for (uint32_t rr = 0; rr < nrows; rr++) {
-            const uint32_t id_rr = __shfl_sync(0xffffffffu, id, rr);
-            float* dst = a.out.dL_dsh + (size_t)id_rr * row_floats;
-            for (int k = lane; k < row_floats; k += 32) {
-                const int coef = k / 3, ch = k - 3 * coef;
-                if (coef < 16) dst[k] += s_w[warp][rr][coef] * s_w[warp][rr][16 + ch];
+        // 4 rows per trip: the 8 loads of a trip are issued before the first add (the read-modify-write is latency bound)
+        for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
+            float* dst[4];
+            float cur[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t rr = min(r0 + u, nrows - 1);
+                const uint32_t id_rr = __shfl_sync(0xffffffffu, id, rr);
+                dst[u] = a.out.dL_dsh + (size_t)id_rr * row_floats;
             }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int k = (int)lane + 32 * h;
+                    cur[u][h] = (r0 + u < nrows && k < row_floats) ? dst[u][k] : 0.f;
+                }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int k = (int)lane + 32 * h;
+                    if (r0 + u < nrows && k < row_floats) {
+                        const int coef = k / 3, ch = k - 3 * coef;
+                        if (coef < 16) dst[u][k] = cur[u][h] + s_w[warp][r0 + u][coef] * s_w[warp][r0 + u][16 + ch];
+                    }
+                }
         }
     }
     if (!valid) return;

@@ -155,11 +155,16 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint
     __syncthreads();
 
     const uint32_t wbase = tile_base + warp * RADIX_WARP_ITEMS;
-    uint32_t key[RADIX_PER_THREAD];
+    uint32_t key[RADIX_PER_THREAD], val[RADIX_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < RADIX_PER_THREAD; k++) { // all 32 loads of the thread are in flight together
+        const uint32_t i = wbase + k * 32 + lane;
+        key[k] = i < n ? keys_in[i] : 0xffffffffu;
+        val[k] = i < n ? vals_in[i] : 0u;
+    }
 #pragma unroll
     for (int k = 0; k < RADIX_PER_THREAD; k++) {
         const uint32_t i = wbase + k * 32 + lane;
-        key[k] = i < n ? keys_in[i] : 0xffffffffu;
         if (i < n) atomicAdd(&s_cnt[warp][(key[k] >> shift) & mask], 1u);
     }
     __syncthreads();
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint
         __syncwarp();
         if (valid) {
             s_keys[pos] = key[k];
-            s_vals[pos] = vals_in[i];
+            s_vals[pos] = val[k];
         }
     }
     __syncthreads();

@@ -110,6 +110,29 @@ class FlatGradients:
     def allreduce(self, dist, group=None):
         dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
 
+    def zero_async(self):
+        """Zero the buffer on a side stream (call at the START of a step, when last step's gradients have been consumed): the
+        1.46 GB fill then overlaps the step's forward/backward instead of sitting in front of the packet rebuild."""
+        if not self.buffer.is_cuda:
+            self.buffer.zero_()
+            return
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.buffer.device)
+        self._side.wait_stream(torch.cuda.current_stream(self.buffer.device))
+        with torch.cuda.stream(self._side):
+            self.buffer.zero_()
+            self._zeroed = torch.cuda.Event()
+            self._zeroed.record(self._side)
+
+    def wait_zeroed(self):
+        """Make the current stream wait for zero_async(); falls back to a synchronous fill if it was not called."""
+        ev = getattr(self, "_zeroed", None)
+        if ev is None:
+            self.buffer.zero_()
+        else:
+            torch.cuda.current_stream(self.buffer.device).wait_event(ev)
+            self._zeroed = None
+
 
 def native_view_backward(D, leaves, rs, fwd, upstream, flat, first, means2D_grad=None):
     """Backward of one view into the flat buffer: overwrite (zero-fill + visible rows) for the step's first local view,
@@ -162,7 +185,7 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
     else:
         recv = send.view(1, nv, cap, words)
-    flat.buffer.zero_()
+    flat.wait_zeroed()
     out = flat.backward_out()
     for r in range(world):
         for v in range(nv):

@@ -96,24 +96,19 @@ def build(verbose=False):
     os.makedirs(OUT, exist_ok=True)
     dgr = os.path.join(REF, "submodules_local", "diff-gaussian-rasterization")
     knn = os.path.join(REF, "submodules_local", "simple-knn")
-    _build(
-        "ref_dgr_C",
-        [
-            os.path.join(dgr, "cuda_rasterizer", "rasterizer_impl.cu"),
-            os.path.join(dgr, "cuda_rasterizer", "forward.cu"),
-            os.path.join(dgr, "cuda_rasterizer", "backward.cu"),
-            os.path.join(dgr, "rasterize_points.cu"),
-            os.path.join(dgr, "ext.cpp"),
-        ],
-        ["-include", "cstdint", "-I" + os.path.join(HERE, "glm_standin"), "-I" + dgr],
-        verbose,
-    )
-    _build(
-        "ref_knn_C",
-        [os.path.join(knn, "simple_knn.cu"), os.path.join(knn, "spatial.cu"), os.path.join(knn, "ext.cpp")],
-        ["-include", "cfloat", "-include", "cstdint", "-I" + knn],
-        verbose,
-    )
+    from concurrent.futures import ThreadPoolExecutor
+
+    jobs = [
+        ("ref_dgr_C",
+         [os.path.join(dgr, "cuda_rasterizer", "rasterizer_impl.cu"), os.path.join(dgr, "cuda_rasterizer", "forward.cu"),
+          os.path.join(dgr, "cuda_rasterizer", "backward.cu"), os.path.join(dgr, "rasterize_points.cu"), os.path.join(dgr, "ext.cpp")],
+         ["-include", "cstdint", "-I" + os.path.join(HERE, "glm_standin"), "-I" + dgr]),
+        ("ref_knn_C",
+         [os.path.join(knn, "simple_knn.cu"), os.path.join(knn, "spatial.cu"), os.path.join(knn, "ext.cpp")],
+         ["-include", "cfloat", "-include", "cstdint", "-I" + knn]),
+    ]
+    with ThreadPoolExecutor(max_workers=2) as ex:  # both modules at once; each compiles its sources in parallel too
+        list(ex.map(lambda j: _build(j[0], j[1], j[2], verbose), jobs))
     return True
 
 

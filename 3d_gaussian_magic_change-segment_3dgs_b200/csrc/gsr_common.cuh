@@ -60,7 +60,7 @@ struct ImgState
     uint2* ranges;       // [T]
 };
 
-constexpr int RADIX_ITEMS = 4096;  // keys per radix CTA (256 threads x 16)
+constexpr int RADIX_ITEMS = 2048;  // keys per radix CTA (256 threads x 8)
 constexpr int SCAN_ITEMS = 2048;   // items per scan CTA (256 threads x 8)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

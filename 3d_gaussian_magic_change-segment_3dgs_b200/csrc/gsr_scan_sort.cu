@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 
 // ------------------------------------------------------------------------------------------ radix sort
 constexpr int RADIX_THREADS = 256;
-constexpr int RADIX_PER_THREAD = RADIX_ITEMS / RADIX_THREADS; // 16
-constexpr int RADIX_WARP_ITEMS = RADIX_ITEMS / 8;             // 512 consecutive keys per warp
+constexpr int RADIX_PER_THREAD = RADIX_ITEMS / RADIX_THREADS; // 8
+constexpr int RADIX_WARP_ITEMS = RADIX_ITEMS / 8;             // 256 consecutive keys per warp
 
 // Per-CTA digit histogram, written digit-major: hist[d * nblocks + block].
 // n_dev != nullptr: the element count lives in device memory (grid sized for a capacity, extra CTAs see no keys).
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_
     if (threadIdx.x <= mask) hist[threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// Stable scatter. Warp w of the CTA owns keys [w*512, w*512+512) of the CTA tile and walks them in order, 32 at a
+// Stable scatter. Warp w of the CTA owns keys [w*256, w*256+256) of the CTA tile and walks them in order, 32 at a
 // time; ranks inside a 32-key step come from match.any, ranks across steps / warps from shared counters. Pairs are first
 // placed at their rank INSIDE the CTA tile in shared memory (digit-major), then written out by consecutive threads, so
 // every digit run of the tile is one contiguous, coalesced burst (a direct scatter issues 32 unrelated 4-byte stores per
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint
     const uint32_t wbase = tile_base + warp * RADIX_WARP_ITEMS;
     uint32_t key[RADIX_PER_THREAD], val[RADIX_PER_THREAD];
 #pragma unroll
-    for (int k = 0; k < RADIX_PER_THREAD; k++) { // all 32 loads of the thread are in flight together
+    for (int k = 0; k < RADIX_PER_THREAD; k++) { // all 16 loads of the thread are in flight together
         const uint32_t i = wbase + k * 32 + lane;
         key[k] = i < n ? keys_in[i] : 0xffffffffu;
         val[k] = i < n ? vals_in[i] : 0u;

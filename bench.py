@@ -451,6 +451,25 @@ def main():
         torch.cuda.synchronize()
         comm_ms = c0.elapsed_time(c1) / 5
 
+    # forward-only ms/frame (the second half of BASELINE.json's metric), same workload, rank-local
+    def fwd_only():
+        with torch.no_grad():
+            rs = settings_for(pkg, wl["cams"][0], bg, device)
+            means2D = torch.zeros_like(leaves["means3D"])
+            return rasterize(leaves, means2D, rs)
+
+    for _ in range(5):
+        fwd_only()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    nf = max(10, min(50, args.steps))
+    for _ in range(nf):
+        fwd_only()
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_ms = f0.elapsed_time(f1) / nf
+
     views_total = V * nranks * args.steps
     value = views_total / (ms_dev / 1e3)
     e2e_value = views_total / (ms_e2e / 1e3)
@@ -514,7 +533,7 @@ def main():
         try:
             kern = json.load(open(os.path.join(ROOT, "profiles", "r01_kernels.json")))
             for kname, kv in kern.items():
-                if kname.startswith(dom + "_kernel"):
+                if dom in kname and "_kernel" in kname:  # render_bwd -> render_bwd2_kernel<2> / render_bwd_kernel<2>
                     traffic = kv.get("dram_traffic_bytes")
         except Exception:
             pass
@@ -562,6 +581,7 @@ def main():
                           "unit": "GB/s", "frac": round(bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9 / hbm_peak, 4)},
         "cpu_baseline": cpu_baseline,
         "step_ms": step_stats,
+        "fwd_ms_per_frame": round(fwd_ms, 4),
     }
     if comm_ms is not None:
         gbytes = 61 * 4 * P / 1e9

@@ -228,6 +228,7 @@ struct RenderArgs
 // ---- stage launchers (each defined next to its kernels) ----
 int launch_preprocess_fwd(const PreFwdArgs& a, cudaStream_t s);
 int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
+int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s);
 int launch_block_offsets(const GeomState& g, cudaStream_t s);
 int launch_depth_keys(const GeomState& g, cudaStream_t s);
 int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, const uint32_t* sorted_slots, cudaStream_t s);

@@ -551,12 +551,13 @@ int launch_block_offsets(const GeomState& g, cudaStream_t s)
     block_offsets_kernel<<<1, 1024, 0, s>>>(g); count_launches(1);
     return 0;
 }
-int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
+// Dense gradient tensors are an API requirement (zeros for invisible Gaussians). Whole-tensor fills run at the HBM write peak
+// (measured 7.5 TB/s on B200, vs 3.3 TB/s for a kernel that skips the scattered rows of visible Gaussians); the dense pass then
+// overwrites the ~20% visible rows. The fills do not depend on the compositing backward, so the caller runs them on a side
+// stream while that (issue-bound) kernel executes.
+int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
-    // Dense gradient tensors are an API requirement (zeros for invisible Gaussians). Whole-tensor fills run at the HBM write
-    // peak (measured 7.5 TB/s on B200, vs 3.3 TB/s for a kernel that skips the scattered rows of visible Gaussians); the dense
-    // pass then overwrites the ~20% visible rows.
     const size_t P = (size_t)a.P;
     struct { float* p; size_t floats; } fills[] = {
         {a.out.dL_dsh, P * (size_t)a.M * 3}, {a.out.dL_dmeans3D, P * 3}, {a.out.dL_dmeans2D, P * 3}, {a.out.dL_dopacity, P},
@@ -568,6 +569,12 @@ int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
         for (auto& f : fills)
             if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
     }
+    return 0;
+}
+
+int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
+{
+    if (a.P <= 0) return 0;
     const uint32_t nb = (a.g.slots + BWD_THREADS - 1) / BWD_THREADS; // capacity: V is only known on the device here
     preprocess_bwd_kernel<<<nb, BWD_THREADS, 0, s>>>(a); count_launches(1);
     return 0;

@@ -6,7 +6,12 @@
 // are depth-sorted once on their 32 depth bits, instances are emitted in that order, and only the tile id
 // (<= 16 bits -> 2 passes) is sorted at instance granularity. Both sorts are stable, so the final order equals
 // the reference's (tile, depth, Gaussian id) order bit for bit.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "gsr_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace gsr
 {
@@ -112,23 +117,35 @@ constexpr int RADIX_THREADS = 256;
 constexpr int RADIX_PER_THREAD = RADIX_ITEMS / RADIX_THREADS; // 8
 constexpr int RADIX_WARP_ITEMS = RADIX_ITEMS / 8;             // 256 consecutive keys per warp
 
-// Per-CTA digit histogram, written digit-major: hist[d * nblocks + block].
-// n_dev != nullptr: the element count lives in device memory (grid sized for a capacity, extra CTAs see no keys).
-__global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ n_dev,
-                                                                   int shift, uint32_t mask, uint32_t nblocks, uint32_t* __restrict__ hist)
+// Per-tile digit histogram, written digit-major: hist[d * ntiles + tile]. With rowsum != nullptr the tile's counts are also
+// added to the per-digit totals (used by the fused sort to skip a separate reduction pass).
+__device__ __forceinline__ void tile_hist_body(uint32_t tile, const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t mask,
+                                               uint32_t ntiles, uint32_t* __restrict__ hist, uint32_t* rowsum)
 {
     __shared__ uint32_t s_hist[256];
-    if (n_dev) n = *n_dev;
+    __syncthreads(); // previous use of s_hist (tile loop of the fused sort)
     s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * RADIX_ITEMS;
+    const uint32_t base = tile * RADIX_ITEMS;
 #pragma unroll
     for (int k = 0; k < RADIX_PER_THREAD; k++) {
         const uint32_t i = base + k * RADIX_THREADS + threadIdx.x;
         if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & mask], 1u);
     }
     __syncthreads();
-    if (threadIdx.x <= mask) hist[threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
+    if (threadIdx.x <= mask) {
+        const uint32_t c = s_hist[threadIdx.x];
+        hist[threadIdx.x * ntiles + tile] = c;
+        if (rowsum && c) atomicAdd(&rowsum[threadIdx.x], c);
+    }
+}
+
+// n_dev != nullptr: the element count lives in device memory (grid sized for a capacity, extra CTAs see no keys).
+__global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ n_dev,
+                                                                   int shift, uint32_t mask, uint32_t nblocks, uint32_t* __restrict__ hist)
+{
+    if (n_dev) n = *n_dev;
+    tile_hist_body(blockIdx.x, keys, n, shift, mask, nblocks, hist, nullptr);
 }
 
 // Stable scatter. Warp w of the CTA owns keys [w*256, w*256+256) of the CTA tile and walks them in order, 32 at a
@@ -136,19 +153,18 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_hist_kernel(const uint32_
 // placed at their rank INSIDE the CTA tile in shared memory (digit-major), then written out by consecutive threads, so
 // every digit run of the tile is one contiguous, coalesced burst (a direct scatter issues 32 unrelated 4-byte stores per
 // warp instruction).
-__global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
-                                                                      const uint32_t* __restrict__ n_dev, int shift, uint32_t mask, uint32_t nblocks,
-                                                                      const uint32_t* __restrict__ offsets /* scanned hist */)
+__device__ __forceinline__ void tile_scatter_body(uint32_t tile, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                                                  uint32_t mask, uint32_t nblocks, const uint32_t* __restrict__ offsets /* scanned hist */)
 {
     __shared__ uint32_t s_cnt[8][256];
     __shared__ uint32_t s_gbase[256];
     __shared__ uint32_t s_keys[RADIX_ITEMS];
     __shared__ uint32_t s_vals[RADIX_ITEMS];
     __shared__ uint32_t s_warp[8];
-    if (n_dev) n = *n_dev;
-    const uint32_t tile_base = blockIdx.x * RADIX_ITEMS;
+    const uint32_t tile_base = tile * RADIX_ITEMS;
     if (tile_base >= n) return;
+    __syncthreads(); // previous tile of the fused sort has left shared memory
     const uint32_t tile_n = min((uint32_t)RADIX_ITEMS, n - tile_base);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 8 * 256; i += RADIX_THREADS) (&s_cnt[0][0])[i] = 0;
@@ -194,7 +210,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint
     if (threadIdx.x <= mask) {
 #pragma unroll
         for (int w = 0; w < 8; w++) s_cnt[w][threadIdx.x] = dstart + wpre[w]; // rank base inside the tile
-        s_gbase[threadIdx.x] = offsets[threadIdx.x * nblocks + blockIdx.x] - dstart;
+        s_gbase[threadIdx.x] = offsets[threadIdx.x * nblocks + tile] - dstart;
     }
     __syncthreads();
 #pragma unroll
@@ -221,6 +237,81 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint
         const uint32_t g = s_gbase[(kk >> shift) & mask] + i;
         keys_out[g] = kk;
         vals_out[g] = s_vals[i];
+    }
+}
+
+__global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                                                                      const uint32_t* __restrict__ n_dev, int shift, uint32_t mask, uint32_t nblocks,
+                                                                      const uint32_t* __restrict__ offsets)
+{
+    if (n_dev) n = *n_dev;
+    tile_scatter_body(blockIdx.x, keys_in, vals_in, keys_out, vals_out, n, shift, mask, nblocks, offsets);
+}
+
+// ------------------------------------------------------------------------------------------ fused (cooperative) sort
+// All passes of one sort in ONE cooperative launch: per pass  tile histograms (+ per-digit totals by atomics) | grid.sync |
+// per-digit row scans | grid.sync | stable scatter | grid.sync.  A 4-pass sort of ~1 M pairs is 16 dependent tiny launches in
+// the multi-kernel path (~12 us each, mostly launch/drain latency); here it is one launch and 12 grid barriers.
+struct RadixCoopArgs
+{
+    uint32_t* keys[2];
+    uint32_t* vals[2];
+    uint32_t n;
+    const uint32_t* n_dev;
+    int passes, digit_bits;
+    uint32_t* hist;   // [bins * ntiles]
+    uint32_t* rowsum; // [2][256], zeroed by the host before the launch
+};
+
+__global__ void __launch_bounds__(RADIX_THREADS) radix_sort_coop_kernel(const RadixCoopArgs a)
+{
+    __shared__ uint32_t s_scan[8];
+    __shared__ uint32_t s_base;
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t n = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    const uint32_t ntiles = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    const uint32_t bins = 1u << a.digit_bits, mask = bins - 1;
+    int cur = 0;
+    for (int p = 0; p < a.passes; p++) {
+        const int shift = p * a.digit_bits;
+        uint32_t* rowsum = a.rowsum + (p & 1) * 256;
+        if (blockIdx.x == 0) a.rowsum[((p + 1) & 1) * 256 + threadIdx.x] = 0; // next pass's totals (idle during this pass)
+        // ---- tile histograms ----
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) tile_hist_body(t, a.keys[cur], n, shift, mask, ntiles, a.hist, rowsum);
+        grid.sync();
+        // ---- digit d: exclusive scan of its row, offset by the totals of the smaller digits ----
+        for (uint32_t d = blockIdx.x; d < bins; d += gridDim.x) {
+            uint32_t part = (threadIdx.x < d) ? rowsum[threadIdx.x] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            __syncthreads();
+            if ((threadIdx.x & 31u) == 0) s_scan[threadIdx.x >> 5] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t b = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) b += s_scan[w];
+                s_base = b;
+            }
+            __syncthreads();
+            uint32_t running = s_base;
+            uint32_t* row = a.hist + (size_t)d * ntiles;
+            for (uint32_t c0 = 0; c0 < ntiles; c0 += RADIX_THREADS) {
+                const uint32_t i = c0 + threadIdx.x;
+                const uint32_t v = i < ntiles ? row[i] : 0u;
+                uint32_t total;
+                const uint32_t excl = block_excl_scan_256(v, s_scan, total);
+                if (i < ntiles) row[i] = running + excl;
+                running += total;
+            }
+        }
+        grid.sync();
+        // ---- stable scatter ----
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+            tile_scatter_body(t, a.keys[cur], a.vals[cur], a.keys[cur ^ 1], a.vals[cur ^ 1], n, shift, mask, ntiles, a.hist);
+        grid.sync();
+        cur ^= 1;
     }
 }
 } // namespace
@@ -252,6 +343,34 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits
     if (hwords + pwords > hist_words) {
         set_error("radix_sort_pairs: histogram workspace too small (%zu > %zu words)", hwords + pwords, hist_words);
         return GSR_ERR_INVALID_ARGUMENT;
+    }
+    // Fused cooperative sort (one launch for all passes), opt-in with GSR_SORT_COOP=1. Measured on B200 at cfg3 it is NOT faster
+    // than the multi-kernel path (binning 0.585 ms vs 0.532 ms: the grid barriers and the per-CTA tile loops cost more than the
+    // launch latency they remove, because the sorts are enqueued ahead of the GPU anyway), so the multi-kernel path is the default.
+    static const int coop_mode = getenv("GSR_SORT_COOP") ? atoi(getenv("GSR_SORT_COOP")) : 0;
+    if (coop_mode && hwords + 512 <= hist_words) {
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_coop_kernel, RADIX_THREADS, 0);
+        if (coop && sms > 0 && per_sm > 0) {
+            RadixCoopArgs ca;
+            ca.keys[0] = keys[0]; ca.keys[1] = keys[1]; ca.vals[0] = vals[0]; ca.vals[1] = vals[1];
+            ca.n = n; ca.n_dev = n_dev; ca.passes = passes; ca.digit_bits = digit_bits;
+            ca.hist = hist; ca.rowsum = hist + hwords;
+            GSR_CUDA(cudaMemsetAsync(ca.rowsum, 0, 512 * sizeof(uint32_t), s));
+            uint32_t want = nb > bins ? nb : bins;
+            uint32_t grid = (uint32_t)(sms * per_sm);
+            if (grid > want) grid = want;
+            void* kargs[] = {(void*)&ca};
+            cudaError_t e = cudaLaunchCooperativeKernel((const void*)radix_sort_coop_kernel, dim3(grid), dim3(RADIX_THREADS), kargs, 0, s);
+            if (e == cudaSuccess) {
+                count_launches(1);
+                return passes & 1;
+            }
+            (void)cudaGetLastError(); // fall back to the multi-kernel path
+        }
     }
     uint32_t* partials = hist + hwords;
     int cur = 0;

@@ -58,7 +58,7 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 # every symbol include/gsr.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
-           "gsr_backward_packets", "gsr_apply_packets", "gsr_last_num_visible"]
+           "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_packet_index_words", "gsr_last_num_visible"]
 GSR_PACKET_WORDS = 17
 
 _lib = None
@@ -90,7 +90,13 @@ def lib():
     L.gsr_backward_packets.restype = ctypes.c_int
     L.gsr_backward_packets.argtypes = [ctypes.POINTER(GsrView), ctypes.POINTER(GsrGaussians), ctypes.c_void_p, ctypes.POINTER(GsrState),
                                        ctypes.c_void_p, ctypes.POINTER(GsrPixelGrads), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
-                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.gsr_gather_packets.restype = ctypes.c_int
+    L.gsr_gather_packets.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.POINTER(GsrParamGrads),
+                                     ctypes.c_void_p]
+    L.gsr_packet_index_words.restype = ctypes.c_size_t
+    L.gsr_packet_index_words.argtypes = [ctypes.c_int32]
     L.gsr_apply_packets.restype = ctypes.c_int
     L.gsr_apply_packets.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.POINTER(GsrParamGrads), ctypes.c_void_p]

@@ -343,19 +343,19 @@ extern "C" size_t gsr_backward_scratch_bytes(int32_t P)
 
 static int backward_impl(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                          const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, cudaStream_t s,
-                         uint32_t* packets, uint32_t capacity, uint32_t* count_dev);
+                         uint32_t* packets, uint32_t capacity, uint32_t* count_dev, uint32_t* vis_index);
 
 extern "C" int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                             const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, gsr_stream_t stream_)
 {
-    return backward_impl(view, in, radii, state, alpha, pix, grads, scratch, scratch_bytes, (cudaStream_t)stream_, nullptr, 0, nullptr);
+    return backward_impl(view, in, radii, state, alpha, pix, grads, scratch, scratch_bytes, (cudaStream_t)stream_, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" uint32_t gsr_last_num_visible(void) { return g_last_visible; }
 
 extern "C" int gsr_backward_packets(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                                     const GsrPixelGrads* pix, uint32_t* packets, uint32_t capacity, uint32_t* count_dev, float* dL_dmeans2D,
-                                    void* scratch, size_t scratch_bytes, gsr_stream_t stream_)
+                                    uint32_t* vis_index, void* scratch, size_t scratch_bytes, gsr_stream_t stream_)
 {
     if (!packets || !count_dev) {
         set_error("gsr_backward_packets: packets/count_dev missing");
@@ -368,7 +368,8 @@ extern "C" int gsr_backward_packets(const GsrView* view, const GsrGaussians* in,
     GsrParamGrads g;
     memset(&g, 0, sizeof(g));
     g.dL_dmeans2D = dL_dmeans2D;
-    return backward_impl(view, in, radii, state, alpha, pix, &g, scratch, scratch_bytes, (cudaStream_t)stream_, packets, capacity, count_dev);
+    return backward_impl(view, in, radii, state, alpha, pix, &g, scratch, scratch_bytes, (cudaStream_t)stream_, packets, capacity, count_dev,
+                         vis_index);
 }
 
 extern "C" int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, const float* campos,
@@ -388,9 +389,29 @@ extern "C" int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs
     return 0;
 }
 
+extern "C" size_t gsr_packet_index_words(int32_t P) { return P > 0 ? 2 * (size_t)((P + 31) / 32) : 0; }
+
+extern "C" int gsr_gather_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, int32_t num_views,
+                                  const float* campos, const uint32_t* blobs, size_t blob_stride_words, uint32_t capacity,
+                                  const GsrParamGrads* grads, gsr_stream_t stream_)
+{
+    if (P <= 0) return 0;
+    if (!means3D || !campos || !blobs || capacity < 1 || !grads || sh_coeffs > 16 || sh_degree < 0 || sh_degree > 3 || num_views < 1 ||
+        num_views > 64) {
+        set_error("gsr_gather_packets: invalid argument (1 <= num_views <= 64)");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    GatherPacketsArgs a;
+    a.P = P; a.D = sh_degree; a.M = sh_coeffs; a.S = num_class; a.num_views = num_views; a.means3D = means3D; a.campos = campos;
+    a.blobs = blobs; a.blob_stride = blob_stride_words; a.capacity = capacity; a.out = *grads;
+    launch_gather_packets(a, (cudaStream_t)stream_);
+    GSR_LAUNCHED((cudaStream_t)stream_, false, "gather_packets");
+    return 0;
+}
+
 static int backward_impl(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                          const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, cudaStream_t s,
-                         uint32_t* packets, uint32_t capacity, uint32_t* count_dev)
+                         uint32_t* packets, uint32_t capacity, uint32_t* count_dev, uint32_t* vis_index)
 {
     int rc = validate(view, in);
     if (rc) return rc;
@@ -427,7 +448,7 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     pb.focal_x = W / (2.0f * view->tanfovx);
     pb.radii = radii; pb.g = g; pb.grad_rec = grad_rec; pb.out = *grads;
     pb.colors_precomp_given = in->colors_precomp != nullptr;
-    pb.packets = packets; pb.packet_capacity = capacity; pb.packet_count = count_dev;
+    pb.packets = packets; pb.packet_capacity = capacity; pb.packet_count = count_dev; pb.vis_index = vis_index;
     if (!in->shs) pb.out.dL_dsh = nullptr;
     if (!in->scales) { pb.out.dL_dscales = nullptr; pb.out.dL_drotations = nullptr; }
 

@@ -189,7 +189,20 @@ struct PreBwdArgs
     uint32_t* packets;
     uint32_t packet_capacity;
     uint32_t* packet_count;
+    uint32_t* vis_index;
 };
+
+struct GatherPacketsArgs
+{
+    int P, D, M, S, num_views;
+    const float* means3D;
+    const float* campos;
+    const uint32_t* blobs;
+    size_t blob_stride;
+    uint32_t capacity;
+    GsrParamGrads out;
+};
+int launch_gather_packets(const GatherPacketsArgs& a, cudaStream_t s);
 
 struct ApplyPacketsArgs
 {

@@ -362,6 +362,11 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
                 dRGB.z *= (cb & 4u) ? 0 : 1;
             }
             uint32_t* pk = a.packets + (size_t)r * GSR_PACKET_WORDS;
+            if (a.vis_index) { // order-independent atomics: the index is deterministic
+                const uint32_t W = ((uint32_t)a.P + 31u) >> 5;
+                atomicOr(&a.vis_index[(uint32_t)idx >> 5], 1u << (idx & 31));
+                atomicMin(&a.vis_index[W + ((uint32_t)idx >> 5)], r);
+            }
             pk[0] = (uint32_t)idx;
             float* pf = reinterpret_cast<float*>(pk);
             pf[1] = dRGB.x; pf[2] = dRGB.y; pf[3] = dRGB.z;
@@ -529,6 +534,121 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_packets_kernel(const Appl
     }
 }
 
+// Multi-GPU gradient rebuild, gather form: one thread per Gaussian sums the packets of all views that saw it and writes its dense
+// rows once. A warp owns 32 consecutive Gaussians = one word of every view's visibility index, so "which views, which packet"
+// costs two warp-uniform word loads per view, and the packets a warp needs from one view are adjacent in memory. Compared with
+// one read-modify-write pass per view (apply_packets_kernel) every dense row is touched exactly once and no zero fill is needed.
+constexpr int GATHER_THREADS = 128;
+constexpr int GATHER_GROUP = 8; // views whose index words are loaded together
+constexpr int GATHER_VIEWS = 2; // views whose packets are in flight together
+__global__ void __launch_bounds__(GATHER_THREADS, 5) gather_packets_kernel(const GatherPacketsArgs a)
+{
+    // SH rows are accumulated in shared memory (row stride 49: each lane's row starts in its own bank), which keeps the register
+    // count low enough for 20 warps per SM -- the kernel is a chain of dependent loads, so resident warps are what hides latency.
+    __shared__ float s_sh[GATHER_THREADS / 32][32 * SH_ROW_STRIDE];
+    __shared__ float s_cam[64 * 3];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < a.num_views * 3; i += GATHER_THREADS) s_cam[i] = a.campos[i];
+    const uint32_t id = blockIdx.x * GATHER_THREADS + threadIdx.x;
+    const bool valid = id < (uint32_t)a.P;
+    const uint32_t W = ((uint32_t)a.P + 31u) >> 5, word_i = min(id >> 5, W - 1);
+    const size_t idx_off = (size_t)a.capacity * GSR_PACKET_WORDS;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool want_sh = a.out.dL_dsh && a.M > 0;
+    float* my = &s_sh[warp][lane * SH_ROW_STRIDE];
+#pragma unroll
+    for (int k = 0; k < 48; k++) my[k] = 0.f;
+    float acc[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) acc[k] = 0.f;
+    const size_t i = (size_t)(valid ? id : 0);
+    const float3 pos = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
+    __syncthreads();
+    for (int g0 = 0; g0 < a.num_views; g0 += GATHER_GROUP) {
+        uint32_t bits[GATHER_GROUP], first[GATHER_GROUP];
+#pragma unroll
+        for (int u = 0; u < GATHER_GROUP; u++) {
+            const bool in = g0 + u < a.num_views;
+            const uint32_t* idx = a.blobs + (size_t)(in ? g0 + u : g0) * a.blob_stride + idx_off;
+            bits[u] = in ? __ldg(idx + word_i) : 0u;
+            first[u] = in ? __ldg(idx + W + word_i) : 0u;
+        }
+#pragma unroll
+        for (int r0 = 0; r0 < GATHER_GROUP; r0 += GATHER_VIEWS) {
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < GATHER_VIEWS; u++) any |= bits[r0 + u] != 0u;
+            if (!any) continue; // warp-uniform: none of the 32 Gaussians is visible in these views
+            bool act[GATHER_VIEWS];
+            float f[GATHER_VIEWS][16];
+#pragma unroll
+            for (int u = 0; u < GATHER_VIEWS; u++) { // unconditional loads (inactive lanes read packet 0): all in flight together
+                const int r = min(g0 + r0 + u, a.num_views - 1);
+                const uint32_t pi = first[r0 + u] + __popc(bits[r0 + u] & lt_mask);
+                act[u] = valid && ((bits[r0 + u] >> lane) & 1u) && pi < a.capacity;
+                const uint32_t* pk = a.blobs + (size_t)r * a.blob_stride + (size_t)(act[u] ? pi : 0u) * GSR_PACKET_WORDS;
+#pragma unroll
+                for (int k = 0; k < 16; k++) f[u][k] = __uint_as_float(__ldg(pk + 1 + k));
+            }
+#pragma unroll
+            for (int u = 0; u < GATHER_VIEWS; u++) {
+                if (!act[u]) continue;
+                const int r = g0 + r0 + u;
+#pragma unroll
+                for (int k = 0; k < 13; k++) acc[k] += f[u][3 + k];
+                if (want_sh) {
+                    V3 dir_orig = {pos.x - s_cam[3 * r], pos.y - s_cam[3 * r + 1], pos.z - s_cam[3 * r + 2]};
+                    const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+                    float w[16];
+                    sh_basis(a.D, dir_orig.x / len, dir_orig.y / len, dir_orig.z / len, w);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        my[3 * k + 0] += w[k] * f[u][0];
+                        my[3 * k + 1] += w[k] * f[u][1];
+                        my[3 * k + 2] += w[k] * f[u][2];
+                    }
+                }
+            }
+        }
+    }
+    if (valid) {
+        if (a.out.dL_dmeans3D) {
+            a.out.dL_dmeans3D[3 * i + 0] = acc[0];
+            a.out.dL_dmeans3D[3 * i + 1] = acc[1];
+            a.out.dL_dmeans3D[3 * i + 2] = acc[2];
+        }
+        if (a.out.dL_dopacity) a.out.dL_dopacity[i] = acc[3];
+        if (a.out.dL_dsegments && a.S == 2) {
+            a.out.dL_dsegments[2 * i + 0] = acc[4];
+            a.out.dL_dsegments[2 * i + 1] = acc[5];
+        }
+        if (a.out.dL_dscales) {
+            a.out.dL_dscales[3 * i + 0] = acc[6];
+            a.out.dL_dscales[3 * i + 1] = acc[7];
+            a.out.dL_dscales[3 * i + 2] = acc[8];
+        }
+        if (a.out.dL_drotations) *reinterpret_cast<float4*>(a.out.dL_drotations + 4 * i) = {acc[9], acc[10], acc[11], acc[12]};
+    }
+    if (want_sh) { // 32 consecutive rows of the warp form one contiguous span: fully coalesced
+        __syncwarp();
+        const uint32_t first_row = blockIdx.x * GATHER_THREADS + warp * 32;
+        if (first_row < (uint32_t)a.P) {
+            const uint32_t nrows = min(32u, (uint32_t)a.P - first_row);
+            const int row_floats = a.M * 3;
+            float* dst = a.out.dL_dsh + (size_t)first_row * row_floats;
+            const uint32_t total = nrows * (uint32_t)row_floats;
+            if (row_floats == 48) {
+                for (uint32_t e = lane; e < total; e += 32) dst[e] = s_sh[warp][(e / 48u) * SH_ROW_STRIDE + e % 48u];
+            } else {
+                for (uint32_t e = lane; e < total; e += 32) {
+                    const uint32_t rr = e / (uint32_t)row_floats, k = e - rr * (uint32_t)row_floats;
+                    dst[e] = k < 48 ? s_sh[warp][rr * SH_ROW_STRIDE + k] : 0.f;
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
                                                            uint8_t* __restrict__ present)
 {
@@ -565,6 +685,11 @@ int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
         {a.out.dL_drotations, P * 4}, {a.out.dL_dcov3D, P * 6}};
     if (a.packets) {
         if (a.out.dL_dmeans2D) GSR_CUDA(cudaMemsetAsync(a.out.dL_dmeans2D, 0, P * 3 * sizeof(float), s));
+        if (a.vis_index) {
+            const size_t W = (P + 31) / 32;
+            GSR_CUDA(cudaMemsetAsync(a.vis_index, 0, W * sizeof(uint32_t), s));
+            GSR_CUDA(cudaMemsetAsync(a.vis_index + W, 0xff, W * sizeof(uint32_t), s));
+        }
     } else if (!a.out.accumulate) {
         for (auto& f : fills)
             if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
@@ -583,6 +708,12 @@ int launch_apply_packets(const ApplyPacketsArgs& a, cudaStream_t s)
 {
     if (a.capacity == 0) return 0;
     apply_packets_kernel<<<(a.capacity + APPLY_THREADS - 1) / APPLY_THREADS, APPLY_THREADS, 0, s>>>(a); count_launches(1);
+    return 0;
+}
+int launch_gather_packets(const GatherPacketsArgs& a, cudaStream_t s)
+{
+    if (a.P <= 0) return 0;
+    gather_packets_kernel<<<(a.P + GATHER_THREADS - 1) / GATHER_THREADS, GATHER_THREADS, 0, s>>>(a); count_launches(1);
     return 0;
 }
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s)

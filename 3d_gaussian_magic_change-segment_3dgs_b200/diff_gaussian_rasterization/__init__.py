@@ -227,7 +227,9 @@ def last_num_visible():
 def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, grad_color, grad_segment, grad_depth, grad_alpha, sh,
                              geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None):
     """gsr_backward_packets: the backward of one view as compact per-visible-Gaussian packets (17 words each, see
-    include/gsr.h) instead of dense gradient rows. Returns (packets int32[capacity, 17], count int32[1])."""
+    include/gsr.h) instead of dense gradient rows. Returns (blob, count int32[1]): blob is ONE int32 tensor of
+    capacity * 17 + 2 * ceil(P / 32) words -- the packets followed by the view's visibility index -- i.e. the all-gather
+    payload of the view (see packet_blob_views)."""
     L = _lib.lib()
     device = means3D.device
     P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
@@ -249,15 +251,47 @@ def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, gr
         nscratch = L.gsr_backward_scratch_bytes(P)
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
         cap = max(int(capacity), 1)
-        packets = torch.empty((cap, _lib.GSR_PACKET_WORDS), dtype=torch.int32, device=device)
+        nidx = int(L.gsr_packet_index_words(P))
+        blob = torch.empty(cap * _lib.GSR_PACKET_WORDS + nidx, dtype=torch.int32, device=device)
         count = torch.zeros(1, dtype=torch.int32, device=device)
         t_radii, t_alpha = radii.contiguous(), _prep(alpha, device, "alpha")
         stream = torch.cuda.current_stream(device).cuda_stream
         rc = L.gsr_backward_packets(ctypes.byref(view), ctypes.byref(gin), t_radii.data_ptr(), ctypes.byref(state), t_alpha.data_ptr(),
-                                    ctypes.byref(pix), packets.data_ptr(), cap, count.data_ptr(), _ptr(means2D_grad), scratch.data_ptr(),
-                                    nscratch, stream)
+                                    ctypes.byref(pix), blob.data_ptr(), cap, count.data_ptr(), _ptr(means2D_grad),
+                                    blob.data_ptr() + 4 * cap * _lib.GSR_PACKET_WORDS, scratch.data_ptr(), nscratch, stream)
         _lib.check(rc, "gsr_backward_packets")
-        return packets, count
+        return blob, count
+
+
+def packet_blob_capacity(blob, P):
+    return (blob.numel() - 2 * ((P + 31) // 32)) // _lib.GSR_PACKET_WORDS
+
+
+def packet_blob_views(blob, P):
+    """(packets int32[capacity, 17], visible-bit words int32[W], first-packet-index words int32[W]) of a view blob."""
+    W = (P + 31) // 32
+    cap = packet_blob_capacity(blob, P)
+    n = cap * _lib.GSR_PACKET_WORDS
+    return blob[:n].view(cap, _lib.GSR_PACKET_WORDS), blob[n:n + W], blob[n + W:n + 2 * W]
+
+
+def gather_packets(means3D, campos_all, sh_degree, sh_coeffs, blobs, out, num_class=NUM_CLASS):
+    """gsr_gather_packets: sum the packets of all views (blobs int32[num_views, blob_words], campos_all f32[num_views, 3])
+    into the dense gradient tensors of `out` (native names), writing EVERY row (zeros where no view saw the Gaussian)."""
+    L = _lib.lib()
+    device = means3D.device
+    P = means3D.size(0)
+    assert blobs.dim() == 2 and blobs.is_contiguous() and blobs.dtype == torch.int32
+    nv = int(blobs.size(0))
+    cap = packet_blob_capacity(blobs[0], P)
+    with torch.cuda.device(device):
+        g = lambda n: _ptr(out.get(n))
+        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 0)
+        cp = _prep(campos_all, device, "campos")
+        rc = L.gsr_gather_packets(P, int(sh_degree), int(sh_coeffs), int(num_class), means3D.data_ptr(), nv, cp.data_ptr(),
+                                  blobs.data_ptr(), int(blobs.size(1)), cap, ctypes.byref(pg),
+                                  torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "gsr_gather_packets")
 
 
 def apply_packets(means3D, campos, sh_degree, sh_coeffs, packets, count, out, num_class=NUM_CLASS):

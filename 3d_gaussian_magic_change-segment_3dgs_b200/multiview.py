@@ -153,41 +153,60 @@ def native_view_backward(D, leaves, rs, fwd, upstream, flat, first, means2D_grad
 # and every rank rebuilds + sums the rows locally in the same (rank, view) order, so replicas stay bitwise identical.
 # Traffic per rank: (N-1) x 68 B x V_visible instead of ~2 x 244 B x P.
 # ---------------------------------------------------------------------------------------------------------------------
-def native_view_backward_packets(D, leaves, rs, fwd, upstream, means2D_grad=None):
-    """Backward of one view as packets. Returns (packets int32[V,17], count int32[1], V)."""
+def native_view_backward_packets(D, leaves, rs, fwd, upstream, means2D_grad=None, capacity=0):
+    """Backward of one view as packets. Returns (blob, count int32[1], V): blob = the view's all-gather payload (packets +
+    visibility index, see D.packet_blob_views) with room for max(capacity, V) packets. Passing the exchange's sticky
+    capacity (`state["cap"]` of exchange_packets) lets the blob be all-gathered in place, without a repacking copy."""
     R, color, depth, segment, alpha, radii, geom, binb, img = fwd
     nvis = D.last_num_visible()
-    packets, count = D._backward_packets_native(rs, leaves["means3D"], radii, leaves["segments"], leaves["scales"], leaves["rotations"],
-                                                upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"),
-                                                leaves["shs"], geom, R, binb, img, alpha, capacity=nvis, means2D_grad=means2D_grad)
-    return packets, count, nvis
+    blob, count = D._backward_packets_native(rs, leaves["means3D"], radii, leaves["segments"], leaves["scales"], leaves["rotations"],
+                                             upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"),
+                                             leaves["shs"], geom, R, binb, img, alpha, capacity=max(nvis, int(capacity)),
+                                             means2D_grad=means2D_grad)
+    return blob, count, nvis
 
 
-def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, world, group=None):
-    """local_sets: [(packets, count, V)] of this rank's views, in view order; all_campos[r][v]: camera centre (device [3]) of
-    view v of rank r (every rank knows every camera). Fills flat.buffer with the SUM over all ranks' views."""
+def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, world, group=None, state=None):
+    """local_sets: [(blob, count, V)] of this rank's views, in view order; all_campos[r][v]: camera centre (device [3]) of
+    view v of rank r (every rank knows every camera). Fills flat.buffer with the SUM over all ranks' views: ONE all-gather of
+    the view blobs, then ONE gather pass (gsr_gather_packets) that writes every dense row once -- no zero fill.
+
+    state (optional dict, kept by the caller across steps) holds the sticky blob capacity "cap": when every view of the step
+    fits and was produced with that capacity, the blobs are all-gathered as they are; otherwise they are repacked to the
+    step's maximum and the capacity grows (5% slack) for the following steps."""
     device = flat.buffer.device
     nv = len(local_sets)
     M = leaves["shs"].size(1)
+    P = leaves["means3D"].size(0)
     counts_local = torch.tensor([s[2] for s in local_sets], dtype=torch.int32, device=device)
     if world > 1:
         counts_all = torch.empty(world * nv, dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(counts_all, counts_local, group=group)
     else:
         counts_all = counts_local
-    cap = max(int(counts_all.max().item()), 1)  # the only host read of the exchange
-    words = local_sets[0][0].size(1)
-    send = torch.empty((nv, cap, words), dtype=torch.int32, device=device)
-    for v, (pk, _, n) in enumerate(local_sets):
-        send[v, :n].copy_(pk[:n])
+    need = max(int(counts_all.max().item()), 1)  # the only host read of the exchange
+    sticky = int(state.get("cap", 0)) if state is not None else 0
+    if sticky >= need:
+        cap = sticky
+    else:
+        cap = need
+        if state is not None:
+            state["cap"] = min(P, (int(need * 1.05) + 1023) // 1024 * 1024)
+    nidx = 2 * ((P + 31) // 32)
+    words = cap * 17 + nidx
+    if all(s[0].numel() == words for s in local_sets):
+        send = local_sets[0][0].view(1, words) if nv == 1 else torch.stack([s[0] for s in local_sets])
+    else:  # repack to the common capacity
+        send = torch.empty((nv, words), dtype=torch.int32, device=device)
+        for v, (blob, _, n) in enumerate(local_sets):
+            own = D.packet_blob_capacity(blob, P)
+            send[v, :n * 17].copy_(blob[:n * 17])
+            send[v, cap * 17:].copy_(blob[own * 17:])
     if world > 1:
-        recv = torch.empty((world, nv, cap, words), dtype=torch.int32, device=device)
+        recv = torch.empty((world * nv, words), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
     else:
-        recv = send.view(1, nv, cap, words)
-    flat.wait_zeroed()
-    out = flat.backward_out()
-    for r in range(world):
-        for v in range(nv):
-            D.apply_packets(leaves["means3D"], all_campos[r][v], sh_degree, M, recv[r, v], counts_all[r * nv + v:r * nv + v + 1], out)
+        recv = send
+    campos = torch.stack([all_campos[r][v] for r in range(world) for v in range(nv)]).contiguous()
+    D.gather_packets(leaves["means3D"], campos, sh_degree, M, recv, flat.backward_out())
     return counts_all

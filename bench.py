@@ -246,12 +246,13 @@ def main():
             v.grad = None
 
     e2e_sets = []
+    xstate = {}  # sticky blob capacity of the packet exchange
 
     def allreduce_grads():
         if dist is None:
             return
         if use_packets and e2e_sets:
-            mv.exchange_packets(Dmod, dist, flat, leaves, e2e_sets, all_campos, 3, nranks)
+            mv.exchange_packets(Dmod, dist, flat, leaves, e2e_sets, all_campos, 3, nranks, state=xstate)
             e2e_sets.clear()
             return
         if flat is not None:
@@ -273,21 +274,20 @@ def main():
 
     def step_device_flat():
         """multi-view / multi-GPU step. dense: every view's backward adds into ONE flat gradient buffer, one NCCL all-reduce.
-        packets: every view's backward emits 68-B packets of its visible Gaussians, one NCCL all-gather, local rebuild + sum."""
+        packets: every view's backward emits 68-B packets of its visible Gaussians + an id map, NCCL all-gathers, then one
+        gather pass that sums all views and writes every dense row once."""
         sets = []
-        if use_packets:
-            flat.zero_async()
         for v in range(V):
             rs = settings_for(pkg, wl["cams"][v], bg, device)
             with torch.no_grad():
                 fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"], leaves["scales"],
                                            leaves["rotations"], empty, rs)
                 if use_packets:
-                    sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug))
+                    sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug, capacity=xstate.get("cap", 0)))
                 else:
                     mv.native_view_backward(Dmod, leaves, rs, fwd, ug, flat, first=(v == 0))
         if use_packets:
-            mv.exchange_packets(Dmod, dist, flat, leaves, sets, all_campos, 3, nranks)
+            mv.exchange_packets(Dmod, dist, flat, leaves, sets, all_campos, 3, nranks, state=xstate)
         elif dist is not None:
             flat.allreduce(dist)
 
@@ -321,8 +321,6 @@ def main():
 
     def step_e2e():
         zero_grads()
-        if use_packets:
-            flat.zero_async()
         total = None
         for v in range(V):
             cam = wl["cams"][v]
@@ -346,7 +344,7 @@ def main():
                 with torch.no_grad():
                     pg = {"color": color.grad, "depth": depth.grad}
                     if use_packets:
-                        e2e_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, pg))
+                        e2e_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, pg, capacity=xstate.get("cap", 0)))
                     else:
                         mv.native_view_backward(Dmod, leaves, rs, fwd, pg, flat, first=(v == 0))
             else:
@@ -428,7 +426,7 @@ def main():
     if dist is not None:
         def comm_only():
             if use_packets:
-                mv.exchange_packets(Dmod, dist, flat, leaves, comm_sets, all_campos, 3, nranks)
+                mv.exchange_packets(Dmod, dist, flat, leaves, comm_sets, all_campos, 3, nranks, state=xstate)
             else:
                 flat.allreduce(dist)
         comm_sets = []
@@ -438,7 +436,7 @@ def main():
                     rs = settings_for(pkg, wl["cams"][v], bg, device)
                     fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"],
                                                leaves["scales"], leaves["rotations"], empty, rs)
-                    comm_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug))
+                    comm_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug, capacity=xstate.get("cap", 0)))
         for _ in range(2):
             comm_only()
         torch.cuda.synchronize()
@@ -506,7 +504,10 @@ def main():
 
     roofline = None
     stages = None
-    if args.impl == "ours" and not args.no_stage_profile and rank == 0:
+    if args.impl == "ours" and not args.no_stage_profile:  # every rank runs it (ranks stay in step); rank 0 reports
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
         L.gsr_set_profiling(1)
         acc = {}
         nprof = max(3, min(10, args.steps))
@@ -520,6 +521,8 @@ def main():
             for k, v in pkg._lib.stage_times().items():
                 acc[k] = acc.get(k, 0.0) + v / nprof
         L.gsr_set_profiling(0)
+        if os.environ.get("GSR_BENCH_DEBUG"):
+            print("DEBUG rank", rank, "stages", {k: round(v, 4) for k, v in acc.items()}, file=sys.stderr, flush=True)
         group = {"preprocess_fwd": ["preprocess_fwd"], "binning": ["depth_sort", "emit", "tile_sort", "tile_ranges"], "render_fwd": ["render_fwd"],
                  "render_bwd": ["render_bwd"], "preprocess_bwd": ["preprocess_bwd"]}
         stages = {}
@@ -566,8 +569,8 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d Gaussians SH3, %dx%d, rasterize_gaussians fwd (colour+depth+alpha+segment) + bwd (dL/dcolour, dL/ddepth), "
                                "%d view(s)/rank/step%s" % (args.workload, P, W, Hh, V,
-                                                           (", gradient exchange = NCCL all-gather of 68-B packets of the visible Gaussians + local "
-                                                            "rebuild into the flat buffer" if use_packets else
+                                                           (", gradient exchange = one NCCL all-gather of per-view blobs (68-B packets of the visible Gaussians + "
+                                                            "visibility index), then one gather pass into the flat buffer" if use_packets else
                                                             ", gradients accumulated in one flat buffer (61 floats/Gaussian), one NCCL all-reduce")
                                                            if nranks > 1 else ""),
                    "views_per_rank": V, "l2": "inputs (%.2f GB of parameters) are larger than the 126 MB L2" % (61 * 4 * P / 1e9), "stats": stats,
@@ -586,9 +589,9 @@ def main():
     if comm_ms is not None:
         gbytes = 61 * 4 * P / 1e9
         if use_packets:
-            line["collective"] = {"op": "ncclAllGather of gradient packets (68 B per visible Gaussian per view) + count all-gather + local "
-                                        "rebuild (memset + %d apply kernels)" % (nranks * V),
-                                  "bytes_sent_per_rank": int(68 * stats["V"] * V), "ms": round(comm_ms, 3),
+            line["collective"] = {"op": "count all-gather + ONE ncclAllGather of view blobs (68 B per visible Gaussian + 2 index words per 32 "
+                                        "Gaussians) + ONE gather pass over %d views that writes every dense row once" % (nranks * V),
+                                  "bytes_sent_per_rank": int((68 * xstate.get("cap", stats["V"]) + P // 4) * V), "ms": round(comm_ms, 3),
                                   "dense_allreduce_bytes": int(61 * 4 * P)}
         else:
             line["collective"] = {"op": "1 x ncclAllReduce(sum, fp32) of the flat gradient buffer", "bytes": int(61 * 4 * P),

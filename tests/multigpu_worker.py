@@ -35,6 +35,7 @@ mv.native_view_backward(D, gs, rs, fwd, ug, dense, first=True)
 dense.allreduce(dist)
 # packet path
 flat = mv.FlatGradients(P, dev)
+flat.buffer.fill_(float(rank + 1))  # the gather pass overwrites every row
 sets = [mv.native_view_backward_packets(D, gs, rs, fwd, ug)]
 campos = [[c["campos"].to(dev)] for c in cams]
 mv.exchange_packets(D, dist, flat, gs, sets, campos, 3, world)

@@ -171,9 +171,9 @@ def test_accumulate_mode_sums_views_into_flat_buffer():
 
 
 def test_gradient_packets_rebuild_dense_rows():
-    """gsr_backward_packets + gsr_apply_packets (the multi-GPU exchange format): applying a view's own packets to a zeroed flat
-    buffer reproduces the dense backward (SH rows are rebuilt as basis(direction) x dL/dRGB) up to the fp32 atomic-order noise
-    between two backward runs; two views sum."""
+    """gsr_backward_packets + gsr_gather_packets / gsr_apply_packets (the multi-GPU exchange format): rebuilding dense rows from
+    a view's packets reproduces the dense backward (SH rows are rebuilt as basis(direction) x dL/dRGB) up to the fp32
+    atomic-order noise between two backward runs; two views sum; the gather form overwrites every row."""
     import importlib
 
     Pk = H.pkg()
@@ -200,9 +200,21 @@ def test_gradient_packets_rebuild_dense_rows():
         dense.append(g)
         campos.append(cam["campos"].cuda())
         assert int(sets[-1][1]) == sets[-1][2] == int((radii > 0).sum())
+        pk, bits, first = D.packet_blob_views(sets[-1][0], P)
+        vis_ids = torch.nonzero(radii > 0).flatten()
+        assert torch.equal(pk[:len(vis_ids), 0].long(), vis_ids)  # packets are in ascending Gaussian order
+        vis = torch.zeros(32 * bits.numel(), dtype=torch.bool, device="cuda")
+        vis[:P] = radii > 0
+        grp = vis.view(-1, 32)
+        want_bits = (grp.long() << torch.arange(32, device="cuda")).sum(1)
+        assert torch.equal(bits.long() & 0xFFFFFFFF, want_bits)
+        before = torch.cumsum(grp.sum(1), 0) - grp.sum(1)  # packets before each group of 32
+        nz = grp.any(1)
+        assert torch.equal(first[nz].long(), before[nz])
         assert H.rel_linf(m2, g["means2D"]) <= 2e-5
     names = {"means3D": "means3D", "shs": "sh", "segments": "segments", "opacities": "opacities", "scales": "scales", "rotations": "rotations"}
-    # one view
+    # one view; the gather pass writes every row, so stale contents must not survive
+    flat.buffer.fill_(123.0)
     mv.exchange_packets(D, None, flat, gs, sets[:1], [campos[:1]], 3, world=1)
     for leaf, nat in names.items():
         assert H.rel_linf(flat.views[leaf], dense[0][nat]) <= 2e-5, leaf
@@ -210,6 +222,26 @@ def test_gradient_packets_rebuild_dense_rows():
     inv = ~(dense[0]["means2D"].abs().sum(1) > 0)
     assert float(flat.views["shs"][inv].abs().max()) == 0.0
     # two views of one rank: the sum
+    flat.buffer.fill_(-7.0)
     mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1)
+    for leaf, nat in names.items():
+        assert H.rel_linf(flat.views[leaf], dense[0][nat] + dense[1][nat]) <= 2e-5, leaf
+    # per-view read-modify-write form (gsr_apply_packets) on a zeroed buffer gives the same sums
+    rmw = mv.FlatGradients(P, "cuda")
+    for (blob, cnt, n), cp in zip(sets, campos):
+        D.apply_packets(gs["means3D"], cp, 3, 16, D.packet_blob_views(blob, P)[0], cnt, rmw.backward_out())
+    assert H.rel_linf(rmw.buffer, flat.buffer) <= 1e-6
+    # sticky capacity: the second step's blobs are produced at the exchange's capacity and gathered without repacking
+    st = {}
+    mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1, state=st)
+    assert st["cap"] >= max(s[2] for s in sets)
+    sets2 = []
+    for cam in cams:
+        rs = H.settings(cam, bg)
+        fwd = D._forward_native(gs["means3D"], gs["shs"], e, gs["segments"], gs["opacities"], gs["scales"], gs["rotations"], e, rs)
+        sets2.append(mv.native_view_backward_packets(D, gs, rs, fwd, ug, capacity=st["cap"]))
+    assert all(D.packet_blob_capacity(s[0], P) == st["cap"] for s in sets2)
+    flat.buffer.fill_(5.0)
+    mv.exchange_packets(D, None, flat, gs, sets2, [campos], 3, world=1, state=st)
     for leaf, nat in names.items():
         assert H.rel_linf(flat.views[leaf], dense[0][nat] + dense[1][nat]) <= 2e-5, leaf

@@ -58,8 +58,11 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 # every symbol include/gsr.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
-           "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_packet_index_words", "gsr_last_num_visible"]
+           "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
+           "gsr_peer_free", "gsr_last_num_visible"]
 GSR_PACKET_WORDS = 17
+GSR_PEER_HANDLE_BYTES = 64
+GSR_MAX_GATHER_VIEWS = 64
 
 _lib = None
 
@@ -95,6 +98,18 @@ def lib():
     L.gsr_gather_packets.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.POINTER(GsrParamGrads),
                                      ctypes.c_void_p]
+    L.gsr_gather_packets_v.restype = ctypes.c_int
+    L.gsr_gather_packets_v.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                       ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32,
+                                       ctypes.POINTER(GsrParamGrads), ctypes.c_void_p]
+    L.gsr_peer_alloc.restype = ctypes.c_int
+    L.gsr_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
+    L.gsr_peer_open.restype = ctypes.c_int
+    L.gsr_peer_open.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+    L.gsr_peer_close.restype = ctypes.c_int
+    L.gsr_peer_close.argtypes = [ctypes.c_void_p]
+    L.gsr_peer_free.restype = ctypes.c_int
+    L.gsr_peer_free.argtypes = [ctypes.c_void_p]
     L.gsr_packet_index_words.restype = ctypes.c_size_t
     L.gsr_packet_index_words.argtypes = [ctypes.c_int32]
     L.gsr_apply_packets.restype = ctypes.c_int

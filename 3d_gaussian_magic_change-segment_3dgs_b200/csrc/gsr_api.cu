@@ -2,6 +2,7 @@
 // Host logic mirrors CudaRasterizer::Rasterizer::forward/backward (cuda_rasterizer/rasterizer_impl.cu:198-458)
 // and the torch glue of rasterize_points.cu:35-242, without torch: raw device pointers + a stream.
 #include <stdarg.h>
+#include <string.h>
 
 #include <vector>
 
@@ -391,21 +392,83 @@ extern "C" int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs
 
 extern "C" size_t gsr_packet_index_words(int32_t P) { return P > 0 ? 2 * (size_t)((P + 31) / 32) : 0; }
 
-extern "C" int gsr_gather_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, int32_t num_views,
-                                  const float* campos, const uint32_t* blobs, size_t blob_stride_words, uint32_t capacity,
-                                  const GsrParamGrads* grads, gsr_stream_t stream_)
+extern "C" int gsr_gather_packets_v(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D,
+                                    int32_t num_views, const float* campos, const uint32_t* const* view_ptrs, size_t packet_off_words,
+                                    size_t index_off_words, uint32_t capacity, const GsrParamGrads* grads, gsr_stream_t stream_)
 {
     if (P <= 0) return 0;
-    if (!means3D || !campos || !blobs || capacity < 1 || !grads || sh_coeffs > 16 || sh_degree < 0 || sh_degree > 3 || num_views < 1 ||
-        num_views > 64) {
+    if (!means3D || !campos || !view_ptrs || capacity < 1 || !grads || sh_coeffs > 16 || sh_degree < 0 || sh_degree > 3 || num_views < 1 ||
+        num_views > GSR_MAX_GATHER_VIEWS) {
         set_error("gsr_gather_packets: invalid argument (1 <= num_views <= 64)");
         return GSR_ERR_INVALID_ARGUMENT;
     }
     GatherPacketsArgs a;
     a.P = P; a.D = sh_degree; a.M = sh_coeffs; a.S = num_class; a.num_views = num_views; a.means3D = means3D; a.campos = campos;
-    a.blobs = blobs; a.blob_stride = blob_stride_words; a.capacity = capacity; a.out = *grads;
+    for (int v = 0; v < GSR_MAX_GATHER_VIEWS; v++) a.views[v] = view_ptrs[v < num_views ? v : 0];
+    for (int v = 0; v < num_views; v++)
+        if (!view_ptrs[v]) {
+            set_error("gsr_gather_packets: null view blob");
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+    a.packet_off = packet_off_words; a.index_off = index_off_words; a.capacity = capacity; a.out = *grads;
     launch_gather_packets(a, (cudaStream_t)stream_);
     GSR_LAUNCHED((cudaStream_t)stream_, false, "gather_packets");
+    return 0;
+}
+
+extern "C" int gsr_gather_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, int32_t num_views,
+                                  const float* campos, const uint32_t* blobs, size_t blob_stride_words, uint32_t capacity,
+                                  const GsrParamGrads* grads, gsr_stream_t stream_)
+{
+    if (P <= 0) return 0;
+    if (!blobs || num_views < 1 || num_views > GSR_MAX_GATHER_VIEWS) {
+        set_error("gsr_gather_packets: invalid argument (1 <= num_views <= 64)");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    const uint32_t* ptrs[GSR_MAX_GATHER_VIEWS];
+    for (int v = 0; v < num_views; v++) ptrs[v] = blobs + (size_t)v * blob_stride_words;
+    return gsr_gather_packets_v(P, sh_degree, sh_coeffs, num_class, means3D, num_views, campos, ptrs, 0,
+                                (size_t)capacity * GSR_PACKET_WORDS, capacity, grads, stream_);
+}
+
+extern "C" int gsr_peer_alloc(size_t bytes, void** ptr, void* handle_out)
+{
+    if (!ptr || !handle_out || bytes == 0) {
+        set_error("gsr_peer_alloc: invalid argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == GSR_PEER_HANDLE_BYTES, "handle size");
+    GSR_CUDA(cudaMalloc(ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        set_error("gsr_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return GSR_ERR_CUDA;
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+extern "C" int gsr_peer_open(const void* handle, void** ptr)
+{
+    if (!handle || !ptr) {
+        set_error("gsr_peer_open: invalid argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    GSR_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int gsr_peer_close(void* ptr)
+{
+    if (ptr) GSR_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+extern "C" int gsr_peer_free(void* ptr)
+{
+    if (ptr) GSR_CUDA(cudaFree(ptr));
     return 0;
 }
 

@@ -197,8 +197,8 @@ struct GatherPacketsArgs
     int P, D, M, S, num_views;
     const float* means3D;
     const float* campos;
-    const uint32_t* blobs;
-    size_t blob_stride;
+    const uint32_t* views[GSR_MAX_GATHER_VIEWS]; // one blob per view; local or PEER memory (NVLink loads)
+    size_t packet_off, index_off;                 // word offsets of the packets / of the visibility index inside a blob
     uint32_t capacity;
     GsrParamGrads out;
 };

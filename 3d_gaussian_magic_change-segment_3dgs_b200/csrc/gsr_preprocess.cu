@@ -552,7 +552,6 @@ __global__ void __launch_bounds__(GATHER_THREADS, 5) gather_packets_kernel(const
     const uint32_t id = blockIdx.x * GATHER_THREADS + threadIdx.x;
     const bool valid = id < (uint32_t)a.P;
     const uint32_t W = ((uint32_t)a.P + 31u) >> 5, word_i = min(id >> 5, W - 1);
-    const size_t idx_off = (size_t)a.capacity * GSR_PACKET_WORDS;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const bool want_sh = a.out.dL_dsh && a.M > 0;
     float* my = &s_sh[warp][lane * SH_ROW_STRIDE];
@@ -569,7 +568,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 5) gather_packets_kernel(const
 #pragma unroll
         for (int u = 0; u < GATHER_GROUP; u++) {
             const bool in = g0 + u < a.num_views;
-            const uint32_t* idx = a.blobs + (size_t)(in ? g0 + u : g0) * a.blob_stride + idx_off;
+            const uint32_t* idx = a.views[in ? g0 + u : g0] + a.index_off;
             bits[u] = in ? __ldg(idx + word_i) : 0u;
             first[u] = in ? __ldg(idx + W + word_i) : 0u;
         }
@@ -586,7 +585,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 5) gather_packets_kernel(const
                 const int r = min(g0 + r0 + u, a.num_views - 1);
                 const uint32_t pi = first[r0 + u] + __popc(bits[r0 + u] & lt_mask);
                 act[u] = valid && ((bits[r0 + u] >> lane) & 1u) && pi < a.capacity;
-                const uint32_t* pk = a.blobs + (size_t)r * a.blob_stride + (size_t)(act[u] ? pi : 0u) * GSR_PACKET_WORDS;
+                const uint32_t* pk = a.views[r] + a.packet_off + (size_t)(act[u] ? pi : 0u) * GSR_PACKET_WORDS;
 #pragma unroll
                 for (int k = 0; k < 16; k++) f[u][k] = __uint_as_float(__ldg(pk + 1 + k));
             }

@@ -225,11 +225,12 @@ def last_num_visible():
 
 
 def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, grad_color, grad_segment, grad_depth, grad_alpha, sh,
-                             geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None):
+                             geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None, raw=None):
     """gsr_backward_packets: the backward of one view as compact per-visible-Gaussian packets (17 words each, see
     include/gsr.h) instead of dense gradient rows. Returns (blob, count int32[1]): blob is ONE int32 tensor of
     capacity * 17 + 2 * ceil(P / 32) words -- the packets followed by the view's visibility index -- i.e. the all-gather
-    payload of the view (see packet_blob_views)."""
+    payload of the view (see packet_blob_views). With raw=(packets_ptr, index_ptr) (device addresses, e.g. inside a
+    gsr_peer_alloc buffer; room for `capacity` packets) the view is written there instead and blob is None."""
     L = _lib.lib()
     device = means3D.device
     P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
@@ -251,14 +252,18 @@ def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, gr
         nscratch = L.gsr_backward_scratch_bytes(P)
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
         cap = max(int(capacity), 1)
-        nidx = int(L.gsr_packet_index_words(P))
-        blob = torch.empty(cap * _lib.GSR_PACKET_WORDS + nidx, dtype=torch.int32, device=device)
         count = torch.zeros(1, dtype=torch.int32, device=device)
+        if raw is None:
+            nidx = int(L.gsr_packet_index_words(P))
+            blob = torch.empty(cap * _lib.GSR_PACKET_WORDS + nidx, dtype=torch.int32, device=device)
+            pk_ptr, idx_ptr = blob.data_ptr(), blob.data_ptr() + 4 * cap * _lib.GSR_PACKET_WORDS
+        else:
+            blob, (pk_ptr, idx_ptr) = None, raw
         t_radii, t_alpha = radii.contiguous(), _prep(alpha, device, "alpha")
         stream = torch.cuda.current_stream(device).cuda_stream
         rc = L.gsr_backward_packets(ctypes.byref(view), ctypes.byref(gin), t_radii.data_ptr(), ctypes.byref(state), t_alpha.data_ptr(),
-                                    ctypes.byref(pix), blob.data_ptr(), cap, count.data_ptr(), _ptr(means2D_grad),
-                                    blob.data_ptr() + 4 * cap * _lib.GSR_PACKET_WORDS, scratch.data_ptr(), nscratch, stream)
+                                    ctypes.byref(pix), pk_ptr, cap, count.data_ptr(), _ptr(means2D_grad), idx_ptr, scratch.data_ptr(),
+                                    nscratch, stream)
         _lib.check(rc, "gsr_backward_packets")
         return blob, count
 
@@ -292,6 +297,53 @@ def gather_packets(means3D, campos_all, sh_degree, sh_coeffs, blobs, out, num_cl
                                   blobs.data_ptr(), int(blobs.size(1)), cap, ctypes.byref(pg),
                                   torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "gsr_gather_packets")
+
+
+def gather_packets_v(means3D, campos_all, sh_degree, sh_coeffs, view_ptrs, packet_off_words, index_off_words, capacity, out,
+                     num_class=NUM_CLASS):
+    """gsr_gather_packets_v: the same pass over one blob POINTER per view (device addresses, local or peer memory)."""
+    L = _lib.lib()
+    device = means3D.device
+    P = means3D.size(0)
+    nv = len(view_ptrs)
+    with torch.cuda.device(device):
+        g = lambda n: _ptr(out.get(n))
+        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 0)
+        cp = _prep(campos_all, device, "campos")
+        arr = (ctypes.c_void_p * nv)(*[int(p) for p in view_ptrs])
+        rc = L.gsr_gather_packets_v(P, int(sh_degree), int(sh_coeffs), int(num_class), means3D.data_ptr(), nv, cp.data_ptr(), arr,
+                                    int(packet_off_words), int(index_off_words), int(capacity), ctypes.byref(pg),
+                                    torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "gsr_gather_packets_v")
+
+
+def peer_alloc(nbytes, device):
+    """gsr_peer_alloc on `device`: (device address, 64-byte handle as bytes)."""
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        ptr = ctypes.c_void_p()
+        h = ctypes.create_string_buffer(_lib.GSR_PEER_HANDLE_BYTES)
+        _lib.check(L.gsr_peer_alloc(int(nbytes), ctypes.byref(ptr), h), "gsr_peer_alloc")
+        return int(ptr.value), bytes(h.raw)
+
+
+def peer_open(handle, device):
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        ptr = ctypes.c_void_p()
+        h = ctypes.create_string_buffer(bytes(handle), _lib.GSR_PEER_HANDLE_BYTES)
+        _lib.check(L.gsr_peer_open(h, ctypes.byref(ptr)), "gsr_peer_open")
+        return int(ptr.value)
+
+
+def peer_close(ptr, device):
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().gsr_peer_close(ctypes.c_void_p(ptr)), "gsr_peer_close")
+
+
+def peer_free(ptr, device):
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().gsr_peer_free(ctypes.c_void_p(ptr)), "gsr_peer_free")
 
 
 def apply_packets(means3D, campos, sh_degree, sh_coeffs, packets, count, out, num_class=NUM_CLASS):

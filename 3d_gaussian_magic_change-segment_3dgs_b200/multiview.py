@@ -210,3 +210,81 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
     campos = torch.stack([all_campos[r][v] for r in range(world) for v in range(nv)]).contiguous()
     D.gather_packets(leaves["means3D"], campos, sh_degree, M, recv, flat.backward_out())
     return counts_all
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Peer-memory exchange (NVLink / NVSwitch): every rank writes its views' blobs into a buffer that the other ranks have mapped
+# (gsr_peer_alloc / gsr_peer_open), and after ONE stream-ordered barrier the gather kernel of every rank pulls all ranks'
+# packets straight over NVLink while it sums them -- the transfer IS the kernel's loads: no all-gather, no staging copy, no
+# host read. Blobs are double-buffered: a rank may start writing step s+1 while a slower rank still reads step s.
+# ---------------------------------------------------------------------------------------------------------------------
+class PeerPacketExchange:
+    def __init__(self, D, dist, P, views_per_rank, rank, world, device, capacity=None, group=None):
+        self.D, self.dist, self.P, self.nv, self.rank, self.world, self.device, self.group = D, dist, P, views_per_rank, rank, world, device, group
+        self.capacity = int(capacity) if capacity else P  # packets per view; P always fits
+        W = (P + 31) // 32
+        self.index_off = 0
+        self.packet_off = (2 * W + 31) // 32 * 32  # 128-byte aligned
+        self.blob_words = self.packet_off + self.capacity * 17
+        self.blob_words = (self.blob_words + 31) // 32 * 32
+        nbytes = 4 * self.blob_words * self.nv
+        self.local, self.peers, handles = [], [], []
+        for b in range(2):
+            ptr, h = D.peer_alloc(nbytes, device)
+            self.local.append(ptr)
+            handles.append(h)
+        mine = torch.tensor(list(handles[0] + handles[1]), dtype=torch.uint8, device=device)
+        everyone = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
+        if world > 1:
+            dist.all_gather_into_tensor(everyone, mine, group=group)
+        else:
+            everyone.copy_(mine)
+        everyone = everyone.cpu().view(world, 2, -1)
+        for b in range(2):
+            row = []
+            for r in range(world):
+                row.append(self.local[b] if r == rank else D.peer_open(bytes(everyone[r, b].tolist()), device))
+            self.peers.append(row)
+        self.parity = 0
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self._opened = True
+
+    def blob_ptr(self, base, v):
+        return base + 4 * self.blob_words * v
+
+    def view_backward(self, leaves, rs, fwd, upstream, v, means2D_grad=None):
+        """Backward of this rank's view v of the step, written as a blob into the current peer-visible buffer."""
+        R, color, depth, segment, alpha, radii, geom, binb, img = fwd
+        base = self.blob_ptr(self.local[self.parity], v)
+        _, count = self.D._backward_packets_native(rs, leaves["means3D"], radii, leaves["segments"], leaves["scales"], leaves["rotations"],
+                                                   upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"),
+                                                   leaves["shs"], geom, R, binb, img, alpha, capacity=self.capacity, means2D_grad=means2D_grad,
+                                                   raw=(base + 4 * self.packet_off, base + 4 * self.index_off))
+        return count
+
+    def exchange(self, flat, leaves, all_campos, sh_degree):
+        """Fills flat.buffer with the sum over all ranks' views of the step (all ranks call this after their view_backward
+        calls). all_campos[r][v]: camera centre (device [3]) of view v of rank r."""
+        if self.world > 1:
+            self.dist.all_reduce(self._flag, group=self.group)  # stream-ordered barrier: every rank's blobs are complete
+        ptrs = [self.blob_ptr(self.peers[self.parity][r], v) for r in range(self.world) for v in range(self.nv)]
+        campos = torch.stack([all_campos[r][v] for r in range(self.world) for v in range(self.nv)]).contiguous()
+        self.D.gather_packets_v(leaves["means3D"], campos, sh_degree, leaves["shs"].size(1), ptrs, self.packet_off, self.index_off,
+                                self.capacity, flat.backward_out())
+        self.parity ^= 1
+
+    def close(self):
+        if not getattr(self, "_opened", False):
+            return
+        self._opened = False
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        for b in range(2):
+            for r in range(self.world):
+                if r != self.rank:
+                    self.D.peer_close(self.peers[b][r], self.device)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        for b in range(2):
+            self.D.peer_free(self.local[b], self.device)

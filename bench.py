@@ -178,8 +178,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--views-per-rank", type=int, default=1)
-    ap.add_argument("--grad-exchange", default="packets", choices=["packets", "dense"],
-                    help="N>1: all-gather 68-B gradient packets of the visible Gaussians (default) or all-reduce the dense flat buffer")
+    ap.add_argument("--grad-exchange", default="peer", choices=["peer", "packets", "dense"],
+                    help="N>1: peer = gather kernel pulls every rank's 68-B gradient packets over NVLink peer memory (default); "
+                         "packets = NCCL all-gather of the packets, then the gather kernel; dense = all-reduce of the flat buffer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-profile", action="store_true")
     args = ap.parse_args()
@@ -251,6 +252,9 @@ def main():
     def allreduce_grads():
         if dist is None:
             return
+        if use_peer:
+            px.exchange(flat, leaves, all_campos, 3)
+            return
         if use_packets and e2e_sets:
             mv.exchange_packets(Dmod, dist, flat, leaves, e2e_sets, all_campos, 3, nranks, state=xstate)
             e2e_sets.clear()
@@ -268,8 +272,10 @@ def main():
     empty = torch.empty(0)
 
     use_packets = use_flat and dist is not None and args.grad_exchange == "packets"
+    use_peer = use_flat and dist is not None and args.grad_exchange == "peer"
+    px = mv.PeerPacketExchange(Dmod, dist, P, V, rank, nranks, device) if use_peer else None
     all_campos = None
-    if use_packets:  # every rank knows every camera of the step
+    if use_packets or use_peer:  # every rank knows every camera of the step
         all_campos = [[syn.make_camera(W, Hh, yaw_deg=45.0 * (r * V + v))["campos"].to(device) for v in range(V)] for r in range(nranks)]
 
     def step_device_flat():
@@ -282,11 +288,15 @@ def main():
             with torch.no_grad():
                 fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"], leaves["scales"],
                                            leaves["rotations"], empty, rs)
-                if use_packets:
+                if use_peer:
+                    px.view_backward(leaves, rs, fwd, ug, v)
+                elif use_packets:
                     sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug, capacity=xstate.get("cap", 0)))
                 else:
                     mv.native_view_backward(Dmod, leaves, rs, fwd, ug, flat, first=(v == 0))
-        if use_packets:
+        if use_peer:
+            px.exchange(flat, leaves, all_campos, 3)
+        elif use_packets:
             mv.exchange_packets(Dmod, dist, flat, leaves, sets, all_campos, 3, nranks, state=xstate)
         elif dist is not None:
             flat.allreduce(dist)
@@ -343,7 +353,9 @@ def main():
                 loss.backward()  # pixel gradients only; the rasterizer backward runs natively into the flat buffer
                 with torch.no_grad():
                     pg = {"color": color.grad, "depth": depth.grad}
-                    if use_packets:
+                    if use_peer:
+                        px.view_backward(leaves, rs, fwd, pg, v)
+                    elif use_packets:
                         e2e_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, pg, capacity=xstate.get("cap", 0)))
                     else:
                         mv.native_view_backward(Dmod, leaves, rs, fwd, pg, flat, first=(v == 0))
@@ -425,7 +437,9 @@ def main():
     comm_ms = None
     if dist is not None:
         def comm_only():
-            if use_packets:
+            if use_peer:
+                px.exchange(flat, leaves, all_campos, 3)
+            elif use_packets:
                 mv.exchange_packets(Dmod, dist, flat, leaves, comm_sets, all_campos, 3, nranks, state=xstate)
             else:
                 flat.allreduce(dist)
@@ -549,6 +563,8 @@ def main():
         roofline = {"kernel": "whole step (reference CUDA)", "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src}
 
+    if px is not None:
+        px.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -569,7 +585,9 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d Gaussians SH3, %dx%d, rasterize_gaussians fwd (colour+depth+alpha+segment) + bwd (dL/dcolour, dL/ddepth), "
                                "%d view(s)/rank/step%s" % (args.workload, P, W, Hh, V,
-                                                           (", gradient exchange = one NCCL all-gather of per-view blobs (68-B packets of the visible Gaussians + "
+                                                           (", gradient exchange = peer memory: every rank's gather kernel pulls all ranks' 68-B packets of the visible Gaussians over "
+                                                            "NVLink while summing them into the flat buffer (one stream-ordered barrier, no all-gather)" if use_peer else
+                                                            ", gradient exchange = one NCCL all-gather of per-view blobs (68-B packets of the visible Gaussians + "
                                                             "visibility index), then one gather pass into the flat buffer" if use_packets else
                                                             ", gradients accumulated in one flat buffer (61 floats/Gaussian), one NCCL all-reduce")
                                                            if nranks > 1 else ""),
@@ -588,7 +606,12 @@ def main():
     }
     if comm_ms is not None:
         gbytes = 61 * 4 * P / 1e9
-        if use_packets:
+        if use_peer:
+            line["collective"] = {"op": "4-byte ncclAllReduce as stream-ordered barrier + ONE gather kernel over %d views reading peer blobs "
+                                        "over NVLink (68 B per visible Gaussian + 2 index words per 32 Gaussians per view)" % (nranks * V),
+                                  "bytes_pulled_per_rank": int((68 * stats["V"] + P // 4) * V * (nranks - 1)), "ms": round(comm_ms, 3),
+                                  "dense_allreduce_bytes": int(61 * 4 * P)}
+        elif use_packets:
             line["collective"] = {"op": "count all-gather + ONE ncclAllGather of view blobs (68 B per visible Gaussian + 2 index words per 32 "
                                         "Gaussians) + ONE gather pass over %d views that writes every dense row once" % (nranks * V),
                                   "bytes_sent_per_rank": int((68 * xstate.get("cap", stats["V"]) + P // 4) * V), "ms": round(comm_ms, 3),

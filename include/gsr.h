@@ -162,6 +162,26 @@ int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t n
 int gsr_gather_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, int32_t num_views,
                        const float* campos, const uint32_t* blobs, size_t blob_stride_words, uint32_t capacity,
                        const GsrParamGrads* grads, gsr_stream_t stream);
+/* The same pass over blobs that need not be adjacent and need not be local: view_ptrs[v] (host array of num_views DEVICE
+ * pointers) is the blob of view v, in this GPU's memory or in a PEER GPU's (a pointer from gsr_peer_open). With peer pointers
+ * the gather pulls every rank's packets straight over NVLink: no all-gather, no staging copy. Inside a blob the packets start
+ * at word `packet_off_words` and the visibility index at word `index_off_words`. The caller orders the kernel after the
+ * producers (a stream-ordered barrier across ranks) and keeps the blobs unchanged until every reader is done. */
+#define GSR_MAX_GATHER_VIEWS 64
+int gsr_gather_packets_v(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, int32_t num_views,
+                         const float* campos, const uint32_t* const* view_ptrs, size_t packet_off_words, size_t index_off_words,
+                         uint32_t capacity, const GsrParamGrads* grads, gsr_stream_t stream);
+
+/* Peer-visible device buffers for gsr_gather_packets_v (one process per GPU, same node). gsr_peer_alloc: cudaMalloc on the
+ * current device + its 64-byte inter-process handle (GSR_PEER_HANDLE_BYTES), which the host ships to the other ranks by any
+ * means (torch.distributed all-gather); gsr_peer_open maps a peer's handle into this process (peer access over NVLink);
+ * gsr_peer_close unmaps it; gsr_peer_free releases the owner's allocation. */
+#define GSR_PEER_HANDLE_BYTES 64
+int gsr_peer_alloc(size_t bytes, void** ptr, void* handle_out);
+int gsr_peer_open(const void* handle, void** ptr);
+int gsr_peer_close(void* ptr);
+int gsr_peer_free(void* ptr);
+
 /* Number of visible Gaussians of the most recent gsr_forward on the calling thread. */
 uint32_t gsr_last_num_visible(void);
 

@@ -46,6 +46,21 @@ assert err <= 2e-5, err  # two backward runs: fp32 atomic-order noise
 ref = flat.buffer.clone()
 dist.broadcast(ref, 0)
 assert torch.equal(ref, flat.buffer), "replicas differ"
+# peer-memory path: blobs written into peer-visible buffers, gather kernel pulls them over NVLink (3 steps: both buffers)
+px = mv.PeerPacketExchange(D, dist, P, 1, rank, world, dev)
+for step in range(3):
+    peer = mv.FlatGradients(P, dev)
+    peer.buffer.fill_(-3.0)
+    cnt = px.view_backward(gs, rs, fwd, ug, 0)
+    px.exchange(peer, gs, campos, 3)
+    torch.cuda.synchronize()
+    assert int(cnt) == sets[0][2]
+    err_p = float((peer.buffer - dense.buffer).abs().max()) / float(dense.buffer.abs().max())
+    assert err_p <= 2e-5, (step, err_p)
+    ref = peer.buffer.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(ref, peer.buffer), "peer replicas differ"
+px.close()
 if rank == 0:
     print("multigpu ok: world=%d rel_err=%.3e" % (world, err))
 dist.destroy_process_group()

@@ -390,7 +390,7 @@ extern "C" int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs
     return 0;
 }
 
-extern "C" size_t gsr_packet_index_words(int32_t P) { return P > 0 ? 2 * (size_t)((P + 31) / 32) : 0; }
+extern "C" size_t gsr_packet_index_words(int32_t P) { return P > 0 ? (2 * (size_t)((P + 31) / 32) + 31) / 32 * 32 : 0; }
 
 extern "C" int gsr_gather_packets_v(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D,
                                     int32_t num_views, const float* campos, const uint32_t* const* view_ptrs, size_t packet_off_words,
@@ -427,8 +427,8 @@ extern "C" int gsr_gather_packets(int32_t P, int32_t sh_degree, int32_t sh_coeff
     }
     const uint32_t* ptrs[GSR_MAX_GATHER_VIEWS];
     for (int v = 0; v < num_views; v++) ptrs[v] = blobs + (size_t)v * blob_stride_words;
-    return gsr_gather_packets_v(P, sh_degree, sh_coeffs, num_class, means3D, num_views, campos, ptrs, 0,
-                                (size_t)capacity * GSR_PACKET_WORDS, capacity, grads, stream_);
+    return gsr_gather_packets_v(P, sh_degree, sh_coeffs, num_class, means3D, num_views, campos, ptrs, gsr_packet_index_words(P), 0, capacity,
+                                grads, stream_);
 }
 
 extern "C" int gsr_peer_alloc(size_t bytes, void** ptr, void* handle_out)

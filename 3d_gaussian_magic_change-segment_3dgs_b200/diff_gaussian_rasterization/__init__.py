@@ -228,7 +228,7 @@ def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, gr
                              geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None, raw=None):
     """gsr_backward_packets: the backward of one view as compact per-visible-Gaussian packets (17 words each, see
     include/gsr.h) instead of dense gradient rows. Returns (blob, count int32[1]): blob is ONE int32 tensor of
-    capacity * 17 + 2 * ceil(P / 32) words -- the packets followed by the view's visibility index -- i.e. the all-gather
+    packet_index_words(P) + capacity * 17 words -- the view's visibility index followed by the packets -- i.e. the all-gather
     payload of the view (see packet_blob_views). With raw=(packets_ptr, index_ptr) (device addresses, e.g. inside a
     gsr_peer_alloc buffer; room for `capacity` packets) the view is written there instead and blob is None."""
     L = _lib.lib()
@@ -255,8 +255,8 @@ def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, gr
         count = torch.zeros(1, dtype=torch.int32, device=device)
         if raw is None:
             nidx = int(L.gsr_packet_index_words(P))
-            blob = torch.empty(cap * _lib.GSR_PACKET_WORDS + nidx, dtype=torch.int32, device=device)
-            pk_ptr, idx_ptr = blob.data_ptr(), blob.data_ptr() + 4 * cap * _lib.GSR_PACKET_WORDS
+            blob = torch.empty(packet_blob_words(P, cap), dtype=torch.int32, device=device)
+            pk_ptr, idx_ptr = blob.data_ptr() + 4 * nidx, blob.data_ptr()
         else:
             blob, (pk_ptr, idx_ptr) = None, raw
         t_radii, t_alpha = radii.contiguous(), _prep(alpha, device, "alpha")
@@ -268,16 +268,28 @@ def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, gr
         return blob, count
 
 
+def packet_index_words(P):
+    """gsr_packet_index_words: words reserved at the start of a view blob for the visibility index."""
+    return (2 * ((P + 31) // 32) + 31) // 32 * 32
+
+
+def packet_blob_words(P, capacity):
+    """Words of a view blob with room for `capacity` packets (a multiple of 32, so that stacked blobs stay 128-byte aligned)."""
+    return packet_index_words(P) + (int(capacity) * _lib.GSR_PACKET_WORDS + 31) // 32 * 32
+
+
 def packet_blob_capacity(blob, P):
-    return (blob.numel() - 2 * ((P + 31) // 32)) // _lib.GSR_PACKET_WORDS
+    return (blob.numel() - packet_index_words(P)) // _lib.GSR_PACKET_WORDS
 
 
 def packet_blob_views(blob, P):
-    """(packets int32[capacity, 17], visible-bit words int32[W], first-packet-index words int32[W]) of a view blob."""
+    """(packets int32[capacity, 17], visible-bit words int32[W], first-packet-index words int32[W]) of a view blob (the index
+    is stored as pairs {bits, ~first}; `first` is only meaningful where bits != 0)."""
     W = (P + 31) // 32
+    n = packet_index_words(P)
+    idx = blob[:2 * W].view(W, 2)
     cap = packet_blob_capacity(blob, P)
-    n = cap * _lib.GSR_PACKET_WORDS
-    return blob[:n].view(cap, _lib.GSR_PACKET_WORDS), blob[n:n + W], blob[n + W:n + 2 * W]
+    return blob[n:n + cap * _lib.GSR_PACKET_WORDS].view(cap, _lib.GSR_PACKET_WORDS), idx[:, 0], ~idx[:, 1]
 
 
 def gather_packets(means3D, campos_all, sh_degree, sh_coeffs, blobs, out, num_class=NUM_CLASS):

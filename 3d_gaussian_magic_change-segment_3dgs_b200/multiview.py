@@ -192,16 +192,14 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
         cap = need
         if state is not None:
             state["cap"] = min(P, (int(need * 1.05) + 1023) // 1024 * 1024)
-    nidx = 2 * ((P + 31) // 32)
-    words = cap * 17 + nidx
+    nidx = D.packet_index_words(P)
+    words = D.packet_blob_words(P, cap)
     if all(s[0].numel() == words for s in local_sets):
         send = local_sets[0][0].view(1, words) if nv == 1 else torch.stack([s[0] for s in local_sets])
     else:  # repack to the common capacity
         send = torch.empty((nv, words), dtype=torch.int32, device=device)
         for v, (blob, _, n) in enumerate(local_sets):
-            own = D.packet_blob_capacity(blob, P)
-            send[v, :n * 17].copy_(blob[:n * 17])
-            send[v, cap * 17:].copy_(blob[own * 17:])
+            send[v, :nidx + n * 17].copy_(blob[:nidx + n * 17])
     if world > 1:
         recv = torch.empty((world * nv, words), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
@@ -222,11 +220,9 @@ class PeerPacketExchange:
     def __init__(self, D, dist, P, views_per_rank, rank, world, device, capacity=None, group=None):
         self.D, self.dist, self.P, self.nv, self.rank, self.world, self.device, self.group = D, dist, P, views_per_rank, rank, world, device, group
         self.capacity = int(capacity) if capacity else P  # packets per view; P always fits
-        W = (P + 31) // 32
         self.index_off = 0
-        self.packet_off = (2 * W + 31) // 32 * 32  # 128-byte aligned
-        self.blob_words = self.packet_off + self.capacity * 17
-        self.blob_words = (self.blob_words + 31) // 32 * 32
+        self.packet_off = D.packet_index_words(P)  # 128-byte aligned
+        self.blob_words = D.packet_blob_words(P, self.capacity)
         nbytes = 4 * self.blob_words * self.nv
         self.local, self.peers, handles = [], [], []
         for b in range(2):

@@ -146,18 +146,19 @@ int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* rad
 int gsr_backward_packets(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                          const GsrPixelGrads* pix, uint32_t* packets, uint32_t capacity, uint32_t* count_dev, float* dL_dmeans2D,
                          uint32_t* vis_index, void* scratch, size_t scratch_bytes, gsr_stream_t stream);
-/* vis_index (optional, [2 * W] words, W = gsr_packet_index_words(P) / 2 = ceil(P / 32)): the view's visibility index, written in
- * full. Word w of the first half has bit b set when Gaussian 32 * w + b is visible; word w of the second half is the packet
- * index of the first visible Gaussian of that group (packets are in ascending Gaussian order), so the packet of Gaussian i
- * is  first[i / 32] + popcount(bits[i / 32] & ((1 << (i % 32)) - 1)). */
+/* vis_index (optional, [W][2] words, W = ceil(P / 32); gsr_packet_index_words(P) = 2 * W rounded up to a multiple of 32 words is
+ * the room to reserve for it; must be 8-byte aligned): the view's
+ * visibility index, written in full. Pair w = { bits, ~first }: bit b of `bits` is set when Gaussian 32 * w + b is visible;
+ * `first` is the packet index of the group's first visible Gaussian (packets are in ascending Gaussian order), so the packet
+ * of Gaussian i is  first[i / 32] + popcount(bits[i / 32] & ((1 << (i % 32)) - 1)). A group without visible Gaussians is {0, 0}. */
 size_t gsr_packet_index_words(int32_t P);
 /* ADD the packets of one view (produced with camera centre `campos`, device [3]) into dense gradient rows. */
 int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, const float* campos,
                       const uint32_t* packets, uint32_t capacity, const uint32_t* count_dev, const GsrParamGrads* grads, gsr_stream_t stream);
 /* One pass over all Gaussians that SUMS the packets of `num_views` views (all-gathered from all ranks) into dense gradient
  * rows and WRITES every row (zeros where no view saw the Gaussian): no zero fill, no read-modify-write per view.
- * blobs: num_views view blobs, `blob_stride_words` apart; one blob = [capacity][17] packet words followed by the view's
- * vis_index (2 * ceil(P / 32) words) -- exactly one all-gather payload per view. campos: [num_views][3] (device). Views are
+ * blobs: num_views view blobs, `blob_stride_words` apart; one blob = the view's vis_index (gsr_packet_index_words(P) words)
+ * followed by [capacity][17] packet words -- exactly one all-gather payload per view. campos: [num_views][3] (device). Views are
  * summed in index order on every rank, so replicas end up bitwise identical. dL_dmeans2D / dL_dcolors / dL_dcov3D are ignored. */
 int gsr_gather_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, int32_t num_views,
                        const float* campos, const uint32_t* blobs, size_t blob_stride_words, uint32_t capacity,

@@ -60,14 +60,18 @@ def test_multiview_step_world2_matches_sequential():
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+
+    with socket.socket() as sk:  # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=180) for _ in range(2)]
     for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+        p.join(timeout=180)
+        assert p.exitcode == 0, p.exitcode
     for rank, total, grads, acc, den, mr in results:
         assert abs(total - float(stotal)) <= 1e-4 * abs(float(stotal))
         for k in grads:

@@ -25,6 +25,7 @@ class GsrGaussians(ctypes.Structure):
         ("P", ctypes.c_int32),
         ("means3D", ctypes.c_void_p), ("shs", ctypes.c_void_p), ("colors_precomp", ctypes.c_void_p), ("segments", ctypes.c_void_p),
         ("opacities", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p), ("cov3D_precomp", ctypes.c_void_p),
+        ("shs_rest", ctypes.c_void_p), ("raw_params", ctypes.c_int32),
     ]
 
 
@@ -44,7 +45,8 @@ class GsrPixelGrads(ctypes.Structure):
 class GsrParamGrads(ctypes.Structure):
     _fields_ = [("dL_dmeans3D", ctypes.c_void_p), ("dL_dmeans2D", ctypes.c_void_p), ("dL_dsh", ctypes.c_void_p), ("dL_dcolors", ctypes.c_void_p),
                 ("dL_dsegments", ctypes.c_void_p), ("dL_dopacity", ctypes.c_void_p), ("dL_dscales", ctypes.c_void_p),
-                ("dL_drotations", ctypes.c_void_p), ("dL_dcov3D", ctypes.c_void_p), ("accumulate", ctypes.c_int32)]
+                ("dL_drotations", ctypes.c_void_p), ("dL_dcov3D", ctypes.c_void_p), ("accumulate", ctypes.c_int32),
+                ("dL_dsh_rest", ctypes.c_void_p)]
 
 
 class GsrStateExport(ctypes.Structure):
@@ -60,6 +62,7 @@ SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scr
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
            "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
            "gsr_peer_free", "gsr_last_num_visible"]
+GSR_ABI_VERSION = 2  # include/gsr.h
 GSR_PACKET_WORDS = 17
 GSR_PEER_HANDLE_BYTES = 64
 GSR_MAX_GATHER_VIEWS = 64
@@ -130,8 +133,8 @@ def lib():
     L.gsr_set_profiling.argtypes = [ctypes.c_int]
     L.gsr_get_stage_times.restype = ctypes.c_int
     L.gsr_get_stage_times.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_char_p)]
-    if L.gsr_abi_version() != 1:
-        raise ImportError("libgsr.so ABI version %d != 1" % L.gsr_abi_version())
+    if L.gsr_abi_version() != GSR_ABI_VERSION:
+        raise ImportError("libgsr.so ABI version %d != %d (rebuild: python __graft_entry__.py)" % (L.gsr_abi_version(), GSR_ABI_VERSION))
     _lib = L
     return L
 

@@ -167,6 +167,16 @@ static int validate(const GsrView* view, const GsrGaussians* in)
             return GSR_ERR_INVALID_ARGUMENT;
         }
     }
+    if (in->raw_params) {
+        if (in->cov3D_precomp || !sr) {
+            set_error("raw_params needs scales + rotations (log-scales, un-normalised quaternions), not cov3D_precomp");
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+        if (in->shs && view->sh_coeffs > 1 && !in->shs_rest) {
+            set_error("raw_params with SHs needs shs (features_dc [P,1,3]) and shs_rest (features_rest [P,M-1,3])");
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+    }
     if (view->num_class != 0 && view->num_class != 2) {
         set_error("num_class=%d is not built (the reference is compiled with NUM_CLASS=2; 0 disables segments)", view->num_class);
         return GSR_ERR_UNSUPPORTED;
@@ -240,6 +250,7 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
     pa.P = P; pa.D = view->sh_degree; pa.M = in->shs ? view->sh_coeffs : 0; pa.S = in->segments ? view->num_class : 0;
     pa.means3D = in->means3D; pa.scales = in->scales; pa.scale_modifier = view->scale_modifier; pa.rotations = in->rotations;
     pa.opacities = in->opacities; pa.shs = in->shs; pa.cov3D_precomp = in->cov3D_precomp; pa.colors_precomp = in->colors_precomp;
+    pa.shs_rest = in->shs_rest; pa.raw = in->raw_params;
     pa.segments = in->segments; pa.view = view->viewmatrix; pa.proj = view->projmatrix; pa.campos = view->campos;
     pa.W = W; pa.H = H; pa.tan_fovx = view->tanfovx; pa.tan_fovy = view->tanfovy;
     pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:226-227
@@ -382,6 +393,10 @@ extern "C" int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs
         set_error("gsr_apply_packets: invalid argument");
         return GSR_ERR_INVALID_ARGUMENT;
     }
+    if (grads->dL_dsh_rest) {
+        set_error("gsr_apply_packets: split SH outputs (dL_dsh_rest) are only built in gsr_gather_packets");
+        return GSR_ERR_UNSUPPORTED;
+    }
     ApplyPacketsArgs a;
     a.P = P; a.D = sh_degree; a.M = sh_coeffs; a.S = num_class; a.means3D = means3D; a.campos = campos;
     a.packets = packets; a.capacity = capacity; a.count = count_dev; a.out = *grads;
@@ -505,6 +520,7 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     PreBwdArgs pb;
     pb.P = P; pb.D = view->sh_degree; pb.M = in->shs ? view->sh_coeffs : 0; pb.S = view->num_class;
     pb.means3D = in->means3D; pb.scales = in->scales; pb.scale_modifier = view->scale_modifier; pb.rotations = in->rotations;
+    pb.shs_rest = in->shs_rest; pb.raw = in->raw_params; pb.opacities = in->opacities; pb.segments = in->segments;
     pb.shs = in->shs; pb.cov3D_precomp = in->cov3D_precomp; pb.view = view->viewmatrix; pb.proj = view->projmatrix; pb.campos = view->campos;
     pb.W = W; pb.H = H; pb.tan_fovx = view->tanfovx; pb.tan_fovy = view->tanfovy;
     pb.focal_y = H / (2.0f * view->tanfovy);
@@ -512,7 +528,12 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     pb.radii = radii; pb.g = g; pb.grad_rec = grad_rec; pb.out = *grads;
     pb.colors_precomp_given = in->colors_precomp != nullptr;
     pb.packets = packets; pb.packet_capacity = capacity; pb.packet_count = count_dev; pb.vis_index = vis_index;
-    if (!in->shs) pb.out.dL_dsh = nullptr;
+    if (!in->shs) { pb.out.dL_dsh = nullptr; pb.out.dL_dsh_rest = nullptr; }
+    if (!in->raw_params) pb.out.dL_dsh_rest = nullptr;
+    if (in->raw_params && pb.out.dL_dsh && view->sh_coeffs > 1 && !pb.out.dL_dsh_rest && !packets) {
+        set_error("raw_params: dL_dsh ([P,1,3]) needs dL_dsh_rest ([P,M-1,3])");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
     if (!in->scales) { pb.out.dL_dscales = nullptr; pb.out.dL_drotations = nullptr; }
 
     g_timer.begin(s);

@@ -155,6 +155,8 @@ struct PreFwdArgs
     const float* cov3D_precomp;
     const float* colors_precomp;
     const float* segments;
+    const float* shs_rest; // raw-parameter mode: shs = [P,1,3], shs_rest = [P,M-1,3]
+    int raw;               // activations inside the kernel (GsrGaussians.raw_params)
     const float* view;
     const float* proj;
     const float* campos;
@@ -174,6 +176,10 @@ struct PreBwdArgs
     float scale_modifier;
     const float* rotations;
     const float* shs;
+    const float* shs_rest;  // raw-parameter mode (see PreFwdArgs)
+    const float* opacities; // raw-parameter mode only (logits)
+    const float* segments;  // raw-parameter mode only (logits)
+    int raw;
     const float* cov3D_precomp;
     const float* view;
     const float* proj;

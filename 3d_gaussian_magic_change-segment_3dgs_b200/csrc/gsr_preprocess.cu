@@ -67,8 +67,12 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
 #pragma unroll
                 for (int i = 0; i < 6; i++) cov3D[i] = a.cov3D_precomp[6 * (size_t)idx + i];
             } else {
-                const float3 sc = {a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]};
-                const float4 q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+                float3 sc = {a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]};
+                float4 q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+                if (a.raw) { // fused activations (scene/gaussian_model.py:100-106): exp, normalize
+                    sc = {expf(sc.x), expf(sc.y), expf(sc.z)};
+                    q = act_normalize(q);
+                }
                 cov3d_from_scale_rot(sc, a.scale_modifier, q, cov3D);
             }
             const float3 cov = cov2d_project(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, s_view, nullptr);
@@ -88,19 +92,23 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
                     float3 rgb;
                     if (a.colors_precomp == nullptr) {
                         const float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
-                        rgb = sh_to_rgb(a.D, p_orig, campos, reinterpret_cast<const float3*>(a.shs) + (size_t)idx * a.M, clamp_bits);
+                        const float3* sh3 = reinterpret_cast<const float3*>(a.shs);
+                        const ShCoeffs<float3> sh = a.raw ? ShCoeffs<float3>{sh3 + idx, reinterpret_cast<const float3*>(a.shs_rest) + (size_t)idx * (a.M - 1)}
+                                                          : ShCoeffs<float3>{sh3 + (size_t)idx * a.M, sh3 + (size_t)idx * a.M + 1};
+                        rgb = sh_to_rgb(a.D, p_orig, campos, sh, clamp_bits);
                     } else {
                         rgb = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
                     }
                     float s0 = 0.f, s1 = 0.f;
                     if (a.S == 2 && a.segments != nullptr) {
                         const float2 sg = *reinterpret_cast<const float2*>(a.segments + 2 * (size_t)idx);
-                        s0 = sg.x;
-                        s1 = sg.y;
+                        s0 = a.raw ? act_sigmoid(sg.x) : sg.x;
+                        s1 = a.raw ? act_sigmoid(sg.y) : sg.y;
                     }
+                    const float op = a.raw ? act_sigmoid(a.opacities[idx]) : a.opacities[idx];
                     radius_out = my_radius;
                     A = {point_image.x, point_image.y, conic.x, conic.y};
-                    B = {conic.z, a.opacities[idx], rgb.x, rgb.y};
+                    B = {conic.z, op, rgb.x, rgb.y};
                     C = {rgb.z, p_view.z, s0, s1};
                     rect = {(unsigned short)rmin.x, (unsigned short)rmin.y, (unsigned short)rmax.x, (unsigned short)rmax.y};
                     tiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
 
         const float3 mean = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
         float3 sc = {0.f, 0.f, 0.f};
-        float4 q = {0.f, 0.f, 0.f, 0.f};
+        float4 q = {0.f, 0.f, 0.f, 0.f}, q_raw = {0.f, 0.f, 0.f, 0.f};
         float cov3D[6];
         if (a.cov3D_precomp != nullptr) {
 #pragma unroll
@@ -235,6 +243,11 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
         } else {
             sc = {a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]};
             q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+            if (a.raw) {
+                q_raw = q;
+                sc = {expf(sc.x), expf(sc.y), expf(sc.z)};
+                q = act_normalize(q);
+            }
             cov3d_from_scale_rot(sc, a.scale_modifier, q, cov3D); // same bits as the forward's (recomputed, not stored)
         }
 
@@ -336,8 +349,10 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
             const float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
             const unsigned cb = a.g.clamped[slot];
             V3* sh_row = (a.out.dL_dsh && !a.packets) ? reinterpret_cast<V3*>(my_sh) : nullptr;
-            const float3 d3 = sh_backward(a.D, mean, campos, reinterpret_cast<const V3*>(a.shs) + (size_t)idx * a.M, cb,
-                                          V3{dL_dcolor.x, dL_dcolor.y, dL_dcolor.z}, ShRowWriter{sh_row});
+            const V3* sh3 = reinterpret_cast<const V3*>(a.shs);
+            const ShCoeffs<V3> sh = a.raw ? ShCoeffs<V3>{sh3 + idx, reinterpret_cast<const V3*>(a.shs_rest) + (size_t)idx * (a.M - 1)}
+                                          : ShCoeffs<V3>{sh3 + (size_t)idx * a.M, sh3 + (size_t)idx * a.M + 1};
+            const float3 d3 = sh_backward(a.D, mean, campos, sh, cb, V3{dL_dcolor.x, dL_dcolor.y, dL_dcolor.z}, ShRowWriter{sh_row});
             if (sh_row) // coefficients above the active degree get no gradient
                 for (int k = (a.D + 1) * (a.D + 1); k < a.M; k++) sh_row[k] = V3{0.f, 0.f, 0.f};
             dL_dmean.x += d3.x;
@@ -346,6 +361,15 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
         }
         // ---- scale / rotation path ----
         if (a.scales != nullptr) cov3d_backward(sc, a.scale_modifier, q, dL_dcov3D, dL_dscale, dL_drot);
+        if (a.raw) { // chain rule of the fused activations: gradients w.r.t. the raw parameters
+            dL_dscale = {dL_dscale.x * sc.x, dL_dscale.y * sc.y, dL_dscale.z * sc.z}; // d exp
+            dL_drot = dact_normalize(q_raw, dL_drot);
+            dL_dopacity = dact_sigmoid(act_sigmoid(a.opacities[idx]), dL_dopacity);
+            if (a.S == 2 && a.segments != nullptr) {
+                const float2 sg = *reinterpret_cast<const float2*>(a.segments + 2 * (size_t)idx);
+                dL_dseg = {dact_sigmoid(act_sigmoid(sg.x), dL_dseg.x), dact_sigmoid(act_sigmoid(sg.y), dL_dseg.y)};
+            }
+        }
     }
 
     // ---- SH gradient rows: each 192-B row leaves the warp as whole 128-B + 64-B bursts (a per-thread row write would
@@ -387,8 +411,18 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
         const uint32_t nrows = min(32u, V - (r & ~31u));
         for (uint32_t rr = 0; rr < nrows; rr++) {
             const int id_rr = __shfl_sync(0xffffffffu, idx, rr);
-            float* dst = a.out.dL_dsh + (size_t)id_rr * row_floats;
             const float* src = &s_sh[warp][rr * SH_ROW_STRIDE];
+            if (a.out.dL_dsh_rest) { // raw-parameter mode: coefficient 0 -> features_dc row, the rest -> features_rest row
+                float* dc = a.out.dL_dsh + (size_t)id_rr * 3;
+                float* rest = a.out.dL_dsh_rest + (size_t)id_rr * (row_floats - 3) - 3;
+                if (a.out.accumulate) {
+                    for (int k = lane; k < row_floats; k += 32) (k < 3 ? dc : rest)[k] += src[k];
+                } else {
+                    for (int k = lane; k < row_floats; k += 32) (k < 3 ? dc : rest)[k] = src[k];
+                }
+                continue;
+            }
+            float* dst = a.out.dL_dsh + (size_t)id_rr * row_floats;
             if (a.out.accumulate) {
                 for (int k = lane; k < row_floats; k += 32) dst[k] += src[k];
             } else {
@@ -673,7 +707,16 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
             const int row_floats = a.M * 3;
             float* dst = a.out.dL_dsh + (size_t)first_row * row_floats;
             const uint32_t total = nrows * (uint32_t)row_floats;
-            if (row_floats == 48) {
+            if (a.out.dL_dsh_rest) { // raw-parameter mode: two tensors, each span still contiguous for the warp's 32 rows
+                float* dc = a.out.dL_dsh + (size_t)first_row * 3;
+                float* rest = a.out.dL_dsh_rest + (size_t)first_row * (row_floats - 3);
+                for (uint32_t e = lane; e < nrows * 3u; e += 32) dc[e] = rows[(e / 3u) * SH_ROW_STRIDE + e % 3u];
+                const uint32_t rf = (uint32_t)row_floats - 3u;
+                for (uint32_t e = lane; e < nrows * rf; e += 32) {
+                    const uint32_t rr = e / rf, k = e - rr * rf + 3u;
+                    rest[e] = k < 48 ? rows[rr * SH_ROW_STRIDE + k] : 0.f;
+                }
+            } else if (row_floats == 48) {
                 for (uint32_t e = lane; e < total; e += 32) dst[e] = rows[(e / 48u) * SH_ROW_STRIDE + e % 48u];
             } else {
                 for (uint32_t e = lane; e < total; e += 32) {
@@ -716,7 +759,8 @@ int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
     if (a.P <= 0) return 0;
     const size_t P = (size_t)a.P;
     struct { float* p; size_t floats; } fills[] = {
-        {a.out.dL_dsh, P * (size_t)a.M * 3}, {a.out.dL_dmeans3D, P * 3}, {a.out.dL_dmeans2D, P * 3}, {a.out.dL_dopacity, P},
+        {a.out.dL_dsh, a.out.dL_dsh_rest ? P * 3 : P * (size_t)a.M * 3},
+        {a.out.dL_dsh_rest, P * (size_t)(a.M > 1 ? a.M - 1 : 0) * 3}, {a.out.dL_dmeans3D, P * 3}, {a.out.dL_dmeans2D, P * 3}, {a.out.dL_dopacity, P},
         {a.out.dL_dcolors, P * 3}, {a.out.dL_dsegments, P * (size_t)(a.S > 0 ? a.S : 0)}, {a.out.dL_dscales, P * 3},
         {a.out.dL_drotations, P * 4}, {a.out.dL_dcov3D, P * 6}};
     if (a.packets) {

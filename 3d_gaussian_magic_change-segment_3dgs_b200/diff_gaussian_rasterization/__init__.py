@@ -107,9 +107,12 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, segments, opacitie
                                      raster_settings)
 
 
-def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, rs):
+def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, rs, sh_rest=None, raw_params=False):
     """RasterizeGaussiansCUDA (rasterize_points.cu:35-125) over gsr_forward. Returns the reference's 9-tuple
-    (num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer)."""
+    (num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer).
+
+    raw_params=True (fused activations, GsrGaussians.raw_params): the tensors are the model's RAW parameters -- opacity /
+    segment logits, log-scales, un-normalised quaternions, sh = _features_dc [P,1,3] and sh_rest = _features_rest [P,M-1,3]."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -126,13 +129,19 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
             return 0, z(NUM_CHANNELS), z(1), z(num_class), z(1), torch.zeros(0, dtype=torch.int32, device=device), e(), e(), e()
         keep = {"device": device}
         M = sh.size(1) if (sh is not None and sh.numel() > 0) else 0
+        t_rest = _prep(sh_rest, device, "sh_rest") if raw_params else None
+        if raw_params and M > 0:
+            if M != 1:
+                raise RuntimeError("raw_params: sh must be _features_dc with shape (P, 1, 3)")
+            M += t_rest.size(1) if t_rest is not None else 0
         view = _view_struct(rs, M, num_class, keep)
         t_means = _prep(means3D, device, "means3D")
         t_sh, t_col = _prep(sh, device, "sh"), _prep(colors_precomp, device, "colors_precomp")
         t_seg, t_op = _prep(segments, device, "segments"), _prep(opacities, device, "opacities")
         t_sc, t_rot = _prep(scales, device, "scales"), _prep(rotations, device, "rotations")
         t_cov = _prep(cov3Ds_precomp, device, "cov3Ds_precomp")
-        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), _ptr(t_op), _ptr(t_sc), _ptr(t_rot), _ptr(t_cov))
+        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), _ptr(t_op), _ptr(t_sc), _ptr(t_rot), _ptr(t_cov),
+                           _ptr(t_rest), int(bool(raw_params)))
         color = torch.empty((NUM_CHANNELS, H, W), **opts)
         segment = torch.empty((num_class, H, W), **opts)
         depth = torch.empty((1, H, W), **opts)
@@ -153,9 +162,13 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
 
 
 def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotations, cov3Ds_precomp, grad_color, grad_segment, grad_depth,
-                     grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, needs=None, out=None, accumulate=False):
+                     grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, needs=None, out=None, accumulate=False,
+                     sh_rest=None, raw_params=False, opacities=None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:127-221) over gsr_backward. Returns a dict of dense
     gradients (zeros for invisible Gaussians). `needs` optionally names the gradients to produce.
+
+    raw_params=True: inputs are the raw parameters (see _forward_native; `opacities` = the logits is then required) and the
+    gradients are w.r.t. them; "sh" is [P,1,3] (features_dc) and "sh_rest" [P,M-1,3] (features_rest).
 
     `out` (dict name -> preallocated contiguous fp32 tensor, e.g. views of one flat buffer) makes the kernels write there
     instead of fresh tensors; with `accumulate=True` the rows of visible Gaussians are ADDED to `out` and nothing else is
@@ -164,15 +177,18 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
     device = means3D.device
     P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
     M = sh.size(1) if (sh is not None and sh.numel() > 0) else 0
+    Mrest = sh_rest.size(1) if (raw_params and M > 0 and sh_rest is not None and sh_rest.numel() > 0) else 0
+    M += Mrest
     num_class = segments.size(1) if (segments is not None and segments.numel() > 0) else NUM_CLASS
-    names = ["means3D", "means2D", "sh", "colors_precomp", "segments", "opacities", "scales", "rotations", "cov3Ds_precomp"]
-    want = {n: True for n in names} if needs is None else {n: bool(needs.get(n, False)) for n in names}
-    have = {"sh": M > 0, "colors_precomp": colors_precomp is not None and colors_precomp.numel() > 0,
+    names = ["means3D", "means2D", "sh", "colors_precomp", "segments", "opacities", "scales", "rotations", "cov3Ds_precomp", "sh_rest"]
+    want = {n: True for n in names} if needs is None else {n: bool(needs.get(n, n == "sh_rest" and needs.get("sh", False))) for n in names}
+    have = {"sh": M > 0, "sh_rest": Mrest > 0, "colors_precomp": colors_precomp is not None and colors_precomp.numel() > 0,
             "segments": segments is not None and segments.numel() > 0,
             "scales": scales is not None and scales.numel() > 0, "rotations": rotations is not None and rotations.numel() > 0,
             "cov3Ds_precomp": cov3Ds_precomp is not None and cov3Ds_precomp.numel() > 0}
-    shapes = {"means3D": (P, 3), "means2D": (P, 3), "sh": (P, M, 3), "colors_precomp": (P, 3), "segments": (P, num_class),
-              "opacities": (P, 1), "scales": (P, 3), "rotations": (P, 4), "cov3Ds_precomp": (P, 6)}
+    shapes = {"means3D": (P, 3), "means2D": (P, 3), "sh": (P, 1, 3) if raw_params else (P, M, 3), "colors_precomp": (P, 3),
+              "segments": (P, num_class), "opacities": (P, 1), "scales": (P, 3), "rotations": (P, 4), "cov3Ds_precomp": (P, 6),
+              "sh_rest": (P, Mrest, 3)}
     with torch.cuda.device(device):
         opts = dict(dtype=torch.float32, device=device)
         grads = {}
@@ -197,8 +213,14 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
         t_seg = _prep(segments, device, "segments")
         t_sc, t_rot = _prep(scales, device, "scales"), _prep(rotations, device, "rotations")
         t_cov = _prep(cov3Ds_precomp, device, "cov3Ds_precomp")
-        # opacities are not needed: they live in the saved geometry state (as in the reference, conic_opacity.w)
-        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), t_means.data_ptr(), _ptr(t_sc), _ptr(t_rot), _ptr(t_cov))
+        # classic: opacities are not needed, they live in the saved geometry state (as in the reference, conic_opacity.w);
+        # raw_params: the sigmoid's backward needs the logits
+        t_op = _prep(opacities, device, "opacities") if raw_params else None
+        if raw_params and t_op is None:
+            raise RuntimeError("raw_params backward needs the raw opacities")
+        t_rest = _prep(sh_rest, device, "sh_rest") if raw_params else None
+        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), t_op.data_ptr() if raw_params else t_means.data_ptr(),
+                           _ptr(t_sc), _ptr(t_rot), _ptr(t_cov), _ptr(t_rest), int(bool(raw_params)))
         g_col = _prep(grad_color, device, "grad_color")
         if g_col is None:
             g_col = torch.zeros((NUM_CHANNELS, H, W), **opts)
@@ -206,7 +228,7 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
         pix = GsrPixelGrads(g_col.data_ptr(), _ptr(g_seg), _ptr(g_dep), _ptr(g_alp))
         pg = GsrParamGrads(_ptr(grads["means3D"]), _ptr(grads["means2D"]), _ptr(grads["sh"]), _ptr(grads["colors_precomp"]),
                            _ptr(grads["segments"]), _ptr(grads["opacities"]), _ptr(grads["scales"]), _ptr(grads["rotations"]),
-                           _ptr(grads["cov3Ds_precomp"]), int(bool(accumulate)))
+                           _ptr(grads["cov3Ds_precomp"]), int(bool(accumulate)), _ptr(grads["sh_rest"]))
         state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
         nscratch = L.gsr_backward_scratch_bytes(P)
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
@@ -225,16 +247,17 @@ def last_num_visible():
 
 
 def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, grad_color, grad_segment, grad_depth, grad_alpha, sh,
-                             geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None, raw=None):
+                             geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None, raw=None, raw_params=None):
     """gsr_backward_packets: the backward of one view as compact per-visible-Gaussian packets (17 words each, see
     include/gsr.h) instead of dense gradient rows. Returns (blob, count int32[1]): blob is ONE int32 tensor of
     packet_index_words(P) + capacity * 17 words -- the view's visibility index followed by the packets -- i.e. the all-gather
     payload of the view (see packet_blob_views). With raw=(packets_ptr, index_ptr) (device addresses, e.g. inside a
-    gsr_peer_alloc buffer; room for `capacity` packets) the view is written there instead and blob is None."""
+    gsr_peer_alloc buffer; room for `capacity` packets) the view is written there instead and blob is None.
+    raw_params = {"sh_rest": _features_rest, "opacities": logits}: fused activations, packets carry raw-parameter gradients."""
     L = _lib.lib()
     device = means3D.device
     P, H, W = means3D.size(0), int(rs.image_height), int(rs.image_width)
-    M = sh.size(1)
+    M = sh.size(1) + (raw_params["sh_rest"].size(1) if raw_params else 0)
     num_class = segments.size(1) if (segments is not None and segments.numel() > 0) else NUM_CLASS
     with torch.cuda.device(device):
         opts = dict(dtype=torch.float32, device=device)
@@ -242,7 +265,10 @@ def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, gr
         view = _view_struct(rs, M, num_class, keep)
         t_means, t_sh, t_seg = _prep(means3D, device, "means3D"), _prep(sh, device, "sh"), _prep(segments, device, "segments")
         t_sc, t_rot = _prep(scales, device, "scales"), _prep(rotations, device, "rotations")
-        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), None, _ptr(t_seg), t_means.data_ptr(), _ptr(t_sc), _ptr(t_rot), None)
+        t_rest = _prep(raw_params["sh_rest"], device, "sh_rest") if raw_params else None
+        t_op = _prep(raw_params["opacities"], device, "opacities") if raw_params else t_means
+        gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), None, _ptr(t_seg), t_op.data_ptr(), _ptr(t_sc), _ptr(t_rot), None, _ptr(t_rest),
+                           int(raw_params is not None))
         g_col = _prep(grad_color, device, "grad_color")
         if g_col is None:
             g_col = torch.zeros((NUM_CHANNELS, H, W), **opts)
@@ -303,7 +329,7 @@ def gather_packets(means3D, campos_all, sh_degree, sh_coeffs, blobs, out, num_cl
     cap = packet_blob_capacity(blobs[0], P)
     with torch.cuda.device(device):
         g = lambda n: _ptr(out.get(n))
-        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 0)
+        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 0, g("sh_rest"))
         cp = _prep(campos_all, device, "campos")
         rc = L.gsr_gather_packets(P, int(sh_degree), int(sh_coeffs), int(num_class), means3D.data_ptr(), nv, cp.data_ptr(),
                                   blobs.data_ptr(), int(blobs.size(1)), cap, ctypes.byref(pg),
@@ -320,7 +346,7 @@ def gather_packets_v(means3D, campos_all, sh_degree, sh_coeffs, view_ptrs, packe
     nv = len(view_ptrs)
     with torch.cuda.device(device):
         g = lambda n: _ptr(out.get(n))
-        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 0)
+        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 0, g("sh_rest"))
         cp = _prep(campos_all, device, "campos")
         arr = (ctypes.c_void_p * nv)(*[int(p) for p in view_ptrs])
         rc = L.gsr_gather_packets_v(P, int(sh_degree), int(sh_coeffs), int(num_class), means3D.data_ptr(), nv, cp.data_ptr(), arr,
@@ -420,6 +446,44 @@ class _RasterizeGaussians(torch.autograd.Function):
                 g["cov3Ds_precomp"], None)
 
 
+class _RasterizeGaussiansRaw(torch.autograd.Function):
+    """Fused-activation entry: takes the model's RAW parameters (scene/gaussian_model.py:50-56) and runs
+    get_opacity / get_segment / get_scaling / get_rotation / get_features (:100-124) inside the preprocess kernels, forward
+    and backward; the gradients returned are those autograd would deliver to the raw parameters through the classic API."""
+
+    @staticmethod
+    def forward(ctx, xyz, means2D, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions, raster_settings):
+        e = torch.empty(0)
+        num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer = _forward_native(
+            xyz, features_dc, e, segment_logits, opacity_logits, log_scales, quaternions, e, raster_settings, sh_rest=features_rest,
+            raw_params=True)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii)
+        ctx.save_for_backward(xyz, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions, radii, geomBuffer,
+                              binningBuffer, imgBuffer, alpha)
+        return color, radii, depth, alpha, segment
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha, grad_segment):
+        rs = ctx.raster_settings
+        xyz, f_dc, f_rest, seg, op, sc, rot, radii, geomBuffer, binningBuffer, imgBuffer, alpha = ctx.saved_tensors
+        nig = ctx.needs_input_grad
+        needs = {"means3D": nig[0], "means2D": nig[1], "sh": nig[2] or nig[3], "sh_rest": nig[2] or nig[3], "segments": nig[4],
+                 "opacities": nig[5], "scales": nig[6], "rotations": nig[7]}
+        e = torch.empty(0)
+        g = _backward_native(rs, xyz, radii, e, seg, sc, rot, e, grad_color, grad_segment, grad_depth, grad_alpha, f_dc, geomBuffer,
+                             ctx.num_rendered, binningBuffer, imgBuffer, alpha, needs=needs, sh_rest=f_rest, raw_params=True, opacities=op)
+        return (g["means3D"], g["means2D"], g["sh"], g["sh_rest"], g["segments"], g["opacities"], g["scales"], g["rotations"], None)
+
+
+def rasterize_gaussians_raw(xyz, means2D, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions,
+                            raster_settings):
+    return _RasterizeGaussiansRaw.apply(xyz, means2D, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions,
+                                        raster_settings)
+
+
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
     image_width: int
@@ -492,6 +556,12 @@ class GaussianRasterizer(nn.Module):
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, segments, opacities, scales, rotations, cov3D_precomp,
                                    raster_settings)
+
+    def forward_raw(self, xyz, means2D, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions):
+        """Opt-in fused-activation entry: pass pc._xyz, pc._features_dc, pc._features_rest, pc._segment, pc._opacity,
+        pc._scaling, pc._rotation instead of the get_* properties; same outputs as forward()."""
+        return rasterize_gaussians_raw(xyz, means2D, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions,
+                                       self.raster_settings)
 
 
 def export_state(P, W, H, geomBuffer, binningBuffer, imgBuffer, num_rendered):

@@ -18,6 +18,13 @@ import torch
 LEAVES = ["means3D", "shs", "segments", "opacities", "scales", "rotations"]  # 3+48+2+1+3+4 = 61 floats per Gaussian
 
 
+def sh_coeffs_of(leaves):
+    """SH coefficients per Gaussian of a leaf dict in either layout (shs, or features_dc + features_rest)."""
+    if "shs" in leaves:
+        return leaves["shs"].size(1)
+    return 1 + leaves["features_rest"].size(1)
+
+
 def shard_views(num_views, rank, world):
     """Indices of the views this rank renders."""
     return list(range(rank, num_views, world))
@@ -86,9 +93,11 @@ class FlatGradients:
     """[61 * P] fp32 buffer, tensor-major: means3D | shs | segments | opacities | scales | rotations. `views[name]` are
     contiguous views shaped like the rasterizer inputs; they can be installed as the `.grad` of the leaves."""
 
-    def __init__(self, P, device, sh_coeffs=16, num_class=2):
-        self.shapes = {"means3D": (P, 3), "shs": (P, sh_coeffs, 3), "segments": (P, num_class), "opacities": (P, 1), "scales": (P, 3),
-                       "rotations": (P, 4)}
+    def __init__(self, P, device, sh_coeffs=16, num_class=2, split_sh=False):
+        """split_sh=True: the raw-parameter layout (fused activations): features_dc | features_rest instead of shs."""
+        sh = {"features_dc": (P, 1, 3), "features_rest": (P, sh_coeffs - 1, 3)} if split_sh else {"shs": (P, sh_coeffs, 3)}
+        self.split_sh = split_sh
+        self.shapes = {"means3D": (P, 3), **sh, "segments": (P, num_class), "opacities": (P, 1), "scales": (P, 3), "rotations": (P, 4)}
         n = sum(int(torch.Size(s).numel()) for s in self.shapes.values())
         self.buffer = torch.zeros(n, dtype=torch.float32, device=device)
         self.views, off = {}, 0
@@ -100,7 +109,8 @@ class FlatGradients:
     def backward_out(self, means2D_grad=None):
         """dict for `_backward_native(out=...)` (the native names differ from the leaf names for SH)."""
         v = self.views
-        return {"means3D": v["means3D"], "means2D": means2D_grad, "sh": v["shs"], "colors_precomp": None, "segments": v["segments"],
+        return {"means3D": v["means3D"], "means2D": means2D_grad, "sh": v["features_dc"] if self.split_sh else v["shs"],
+                "sh_rest": v["features_rest"] if self.split_sh else None, "colors_precomp": None, "segments": v["segments"],
                 "opacities": v["opacities"], "scales": v["scales"], "rotations": v["rotations"], "cov3Ds_precomp": None}
 
     def install(self, leaves):
@@ -176,7 +186,7 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
     step's maximum and the capacity grows (5% slack) for the following steps."""
     device = flat.buffer.device
     nv = len(local_sets)
-    M = leaves["shs"].size(1)
+    M = sh_coeffs_of(leaves)
     P = leaves["means3D"].size(0)
     counts_local = torch.tensor([s[2] for s in local_sets], dtype=torch.int32, device=device)
     if world > 1:
@@ -265,7 +275,7 @@ class PeerPacketExchange:
             self.dist.all_reduce(self._flag, group=self.group)  # stream-ordered barrier: every rank's blobs are complete
         ptrs = [self.blob_ptr(self.peers[self.parity][r], v) for r in range(self.world) for v in range(self.nv)]
         campos = torch.stack([all_campos[r][v] for r in range(self.world) for v in range(self.nv)]).contiguous()
-        self.D.gather_packets_v(leaves["means3D"], campos, sh_degree, leaves["shs"].size(1), ptrs, self.packet_off, self.index_off,
+        self.D.gather_packets_v(leaves["means3D"], campos, sh_degree, sh_coeffs_of(leaves), ptrs, self.packet_off, self.index_off,
                                 self.capacity, flat.backward_out())
         self.parity ^= 1
 

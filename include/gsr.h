@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 
 #define GSR_OK 0
 #define GSR_ERR_INVALID_ARGUMENT (-1)
@@ -76,6 +76,15 @@ typedef struct GsrGaussians {
     const float* scales;         /* [P,3] or NULL */
     const float* rotations;      /* [P,4] (w,x,y,z; used un-normalised) or NULL */
     const float* cov3D_precomp;  /* [P,6] or NULL */
+    /* Fused-activation entry (replaces the five torch kernels + the 1.15 GB torch.cat of
+     * scene/gaussian_model.py:100-124 in front of the rasterizer). raw_params != 0: the tensors above are the model's RAW
+     * parameters and the activations run inside the preprocess kernels, forward and backward:
+     *   opacities, segments = logits (sigmoid), scales = log-scales (exp), rotations = un-normalised quaternions
+     *   (x / max(|x|, 1e-12), torch.nn.functional.normalize), shs = _features_dc [P,1,3] and shs_rest = _features_rest
+     *   [P,M-1,3] (the torch.cat is never materialised). Gradients are then w.r.t. the raw parameters, and gsr_backward
+     *   needs `opacities` (raw) as well. cov3D_precomp must be NULL. raw_params == 0: classic behaviour, shs_rest ignored. */
+    const float* shs_rest;
+    int32_t raw_params;
 } GsrGaussians;
 
 /* Forward outputs; every element is written by the kernels (no pre-zeroing needed) when P > 0. */
@@ -116,6 +125,7 @@ typedef struct GsrParamGrads {
     float* dL_drotations; /* [P,4] (needs rotations) */
     float* dL_dcov3D;     /* [P,6] */
     int32_t accumulate;
+    float* dL_dsh_rest;   /* raw_params only: dL_dsh is then [P,1,3] (features_dc) and this is [P,M-1,3] (features_rest) */
 } GsrParamGrads;
 
 int gsr_abi_version(void);

@@ -55,13 +55,17 @@ class GsrStateExport(ctypes.Structure):
                 ("ranges", ctypes.c_void_p), ("n_contrib", ctypes.c_void_p)]
 
 
+class GsrAdamGroup(ctypes.Structure):
+    _fields_ = [("offset", ctypes.c_uint64), ("count", ctypes.c_uint64), ("lr", ctypes.c_float)]
+
+
 ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t)
 
 # every symbol include/gsr.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
            "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
-           "gsr_peer_free", "gsr_last_num_visible"]
+           "gsr_peer_free", "gsr_adam_step", "gsr_last_num_visible"]
 GSR_ABI_VERSION = 2  # include/gsr.h
 GSR_PACKET_WORDS = 17
 GSR_PEER_HANDLE_BYTES = 64
@@ -113,6 +117,9 @@ def lib():
     L.gsr_peer_close.argtypes = [ctypes.c_void_p]
     L.gsr_peer_free.restype = ctypes.c_int
     L.gsr_peer_free.argtypes = [ctypes.c_void_p]
+    L.gsr_adam_step.restype = ctypes.c_int
+    L.gsr_adam_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GsrAdamGroup), ctypes.c_int32,
+                                ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_void_p]
     L.gsr_packet_index_words.restype = ctypes.c_size_t
     L.gsr_packet_index_words.argtypes = [ctypes.c_int32]
     L.gsr_apply_packets.restype = ctypes.c_int

@@ -1,0 +1,147 @@
+// Fused multi-tensor Adam over the flat parameter / gradient buffers.
+// Replaces torch.optim.Adam(l, lr=0.0, eps=1e-15) of scene/gaussian_model.py:166-177: seven parameter groups with their own
+// learning rates, updated by ONE launch that reads p, g, m, v and writes p, m, v once (28 B per parameter; torch's foreach
+// path makes ~8 passes over the same tensors). The arithmetic follows torch.optim.Adam's default (foreach) path op by op in
+// fp32, with the bias corrections evaluated in double on the host like the Python code does:
+//   m = m + (1-b1) * (g - m)                    torch._foreach_lerp_
+//   v = v * b2 ; v = v + (1-b2) * (g * g)       _foreach_mul_, _foreach_addcmul_
+//   d = sqrt(v) / sqrt(1 - b2^t) + eps          _foreach_sqrt, _foreach_div_, _foreach_add_
+//   p = p + (-(lr / (1 - b1^t))) * (m / d)      _foreach_addcdiv_
+#include <math.h>
+#include <stdlib.h>
+
+#include "gsr_common.cuh"
+
+namespace gsr
+{
+namespace
+{
+constexpr int ADAM_THREADS = 256;
+constexpr int ADAM_VEC = 4; // float4 per thread per trip
+constexpr int ADAM_MAX_GROUPS = 16;
+constexpr int ADAM_TRIPS = 4;
+
+struct AdamArgs
+{
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int num_groups;
+    unsigned long long offset[ADAM_MAX_GROUPS];
+    unsigned long long count[ADAM_MAX_GROUPS];
+    unsigned int first_chunk[ADAM_MAX_GROUPS + 1]; // CTA -> group table
+    float neg_step_size[ADAM_MAX_GROUPS];          // -(lr / bias_correction1)
+    float w1, b2, w2, bc2_sqrt, eps;               // 1-b1, b2, 1-b2, sqrt(1-b2^t), eps
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float nss)
+{
+    m = __fmaf_rn(a.w1, g - m, m);
+    v = __fmaf_rn(a.w2, g * g, v * a.b2);
+    // m == 0 (a Gaussian no view has seen yet): torch adds -step * (0 / d) = 0, p keeps its bits. Skipping it also skips the
+    // special-operand slow paths of the IEEE sqrt and divisions, which otherwise cost 1.8x on a step where 80 % of the rows are zero.
+    if (m != 0.f) {
+        const float d = sqrtf(v) / a.bc2_sqrt + a.eps;
+        p = __fmaf_rn(nss, m / d, p);
+    }
+}
+
+template <int TRIPS, bool STREAM>
+__global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a)
+{
+    constexpr int ADAM_CHUNK = ADAM_THREADS * ADAM_VEC * TRIPS; // floats per CTA
+    int grp = 0;
+#pragma unroll 1
+    while (grp + 1 < a.num_groups && blockIdx.x >= a.first_chunk[grp + 1]) grp++;
+    const unsigned long long base = a.offset[grp], n = a.count[grp];
+    const unsigned long long c0 = (unsigned long long)(blockIdx.x - a.first_chunk[grp]) * ADAM_CHUNK;
+    const float nss = a.neg_step_size[grp];
+    float* p = a.p + base;
+    const float* g = a.g + base;
+    float* m = a.m + base;
+    float* v = a.v + base;
+    const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15u) == 0;
+    if (aligned && c0 + ADAM_CHUNK <= n) { // full chunk, 16-byte aligned: 4 x LDG.128 per array in flight per thread
+        float4 P4[TRIPS], G4[TRIPS], M4[TRIPS], V4[TRIPS];
+#pragma unroll
+        for (int t = 0; t < TRIPS; t++) {
+            const unsigned long long i = c0 + (unsigned long long)(t * ADAM_THREADS + threadIdx.x) * ADAM_VEC;
+            if (STREAM) { // every byte is touched once per step: evict-first keeps the stream from churning L2
+                P4[t] = __ldcs(reinterpret_cast<const float4*>(p + i));
+                G4[t] = __ldcs(reinterpret_cast<const float4*>(g + i));
+                M4[t] = __ldcs(reinterpret_cast<const float4*>(m + i));
+                V4[t] = __ldcs(reinterpret_cast<const float4*>(v + i));
+            } else {
+                P4[t] = *reinterpret_cast<const float4*>(p + i);
+                G4[t] = __ldg(reinterpret_cast<const float4*>(g + i));
+                M4[t] = *reinterpret_cast<const float4*>(m + i);
+                V4[t] = *reinterpret_cast<const float4*>(v + i);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TRIPS; t++) {
+            adam_one(P4[t].x, G4[t].x, M4[t].x, V4[t].x, a, nss);
+            adam_one(P4[t].y, G4[t].y, M4[t].y, V4[t].y, a, nss);
+            adam_one(P4[t].z, G4[t].z, M4[t].z, V4[t].z, a, nss);
+            adam_one(P4[t].w, G4[t].w, M4[t].w, V4[t].w, a, nss);
+            const unsigned long long i = c0 + (unsigned long long)(t * ADAM_THREADS + threadIdx.x) * ADAM_VEC;
+            if (STREAM) {
+                __stcs(reinterpret_cast<float4*>(p + i), P4[t]);
+                __stcs(reinterpret_cast<float4*>(m + i), M4[t]);
+                __stcs(reinterpret_cast<float4*>(v + i), V4[t]);
+            } else {
+                *reinterpret_cast<float4*>(p + i) = P4[t];
+                *reinterpret_cast<float4*>(m + i) = M4[t];
+                *reinterpret_cast<float4*>(v + i) = V4[t];
+            }
+        }
+        return;
+    }
+    for (unsigned long long i = c0 + threadIdx.x; i < n && i < c0 + ADAM_CHUNK; i += ADAM_THREADS) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_one(pp, g[i], mm, vv, a, nss);
+        p[i] = pp;
+        m[i] = mm;
+        v[i] = vv;
+    }
+}
+} // namespace
+} // namespace gsr
+
+using namespace gsr;
+
+extern "C" int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const GsrAdamGroup* groups,
+                             int32_t num_groups, double beta1, double beta2, double eps, int32_t step, gsr_stream_t stream_)
+{
+    if (num_groups <= 0) return 0;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !groups || num_groups > ADAM_MAX_GROUPS || step < 1) {
+        set_error("gsr_adam_step: invalid argument (1 <= num_groups <= %d, step >= 1)", ADAM_MAX_GROUPS);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    AdamArgs a;
+    a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.num_groups = num_groups;
+    // Python: bias_correction1 = 1 - beta1 ** step; step_size = lr / bias_correction1; bias_correction2_sqrt = sqrt(1 - beta2 ** step)
+    const double b1 = beta1, b2 = beta2; // doubles end to end: (float)0.9 would turn 1 - beta1 into 0.10000002
+    const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+    a.w1 = (float)(1.0 - b1); a.b2 = (float)b2; a.w2 = (float)(1.0 - b2); a.bc2_sqrt = (float)sqrt(bc2); a.eps = (float)eps;
+    // 4 x LDG.128 per array per thread; 1, 2 or 4 trips and evict-first hints all measure 1.47 ms (6.97 TB/s) at 61 x 6M floats
+    const unsigned long long ADAM_CHUNK = (unsigned long long)ADAM_THREADS * ADAM_VEC * ADAM_TRIPS;
+    unsigned long long chunks = 0;
+    for (int i = 0; i < num_groups; i++) {
+        a.offset[i] = groups[i].offset; a.count[i] = groups[i].count;
+        a.neg_step_size[i] = (float)(-((double)groups[i].lr / bc1));
+        a.first_chunk[i] = (unsigned int)chunks;
+        chunks += (groups[i].count + ADAM_CHUNK - 1) / ADAM_CHUNK;
+    }
+    a.first_chunk[num_groups] = (unsigned int)chunks;
+    if (chunks == 0) return 0;
+    if (chunks > 0x7fffffffull) {
+        set_error("gsr_adam_step: too many parameters");
+        return GSR_ERR_UNSUPPORTED;
+    }
+    const unsigned int nb = (unsigned int)chunks;
+    cudaStream_t s = (cudaStream_t)stream_;
+    adam_kernel<ADAM_TRIPS, false><<<nb, ADAM_THREADS, 0, s>>>(a); count_launches(1);
+    return after_launch((cudaStream_t)stream_, false, "adam");
+}

@@ -193,6 +193,19 @@ int gsr_peer_open(const void* handle, void** ptr);
 int gsr_peer_close(void* ptr);
 int gsr_peer_free(void* ptr);
 
+/* Fused multi-tensor Adam over flat buffers (replaces torch.optim.Adam(l, lr=0.0, eps=1e-15) and its seven
+ * parameter groups, scene/gaussian_model.py:166-177, following the default foreach path op by op in fp32). params / grads /
+ * exp_avg / exp_avg_sq are flat fp32 buffers of the same layout; group g covers elements [offset, offset + count) with
+ * learning rate lr. step = the 1-based step number (bias corrections are evaluated in double on the host, as Python does).
+ * One launch; 28 bytes of HBM traffic per parameter. No weight decay, no amsgrad (the reference uses neither). */
+typedef struct GsrAdamGroup {
+    uint64_t offset;
+    uint64_t count;
+    float lr;
+} GsrAdamGroup;
+int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const GsrAdamGroup* groups, int32_t num_groups,
+                  double beta1, double beta2, double eps, int32_t step, gsr_stream_t stream);
+
 /* Number of visible Gaussians of the most recent gsr_forward on the calling thread. */
 uint32_t gsr_last_num_visible(void);
 

@@ -632,7 +632,7 @@ def main():
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def run_cpu_baseline(syn, workload, row_stride=17):
+def run_cpu_baseline(syn, workload, row_stride=1):
     """Oracle B (C + OpenMP, all host cores) on a bounded sample of the SAME workload: full per-Gaussian stages and binning,
     compositing forward+backward on every `row_stride`-th tile row; the compositing time is scaled by the sampled
     fraction of tile instances. Reported baseline, not a target."""

@@ -25,6 +25,22 @@ def sh_coeffs_of(leaves):
     return 1 + leaves["features_rest"].size(1)
 
 
+def _sh_and_raw(leaves):
+    """(sh tensor, raw_params dict or None) of a leaf dict: the classic layout (activated values, "shs") or the raw-parameter
+    layout of optim.FlatParameters ("features_dc" + "features_rest", logits / log-scales / un-normalised quaternions)."""
+    if "shs" in leaves:
+        return leaves["shs"], None
+    return leaves["features_dc"], {"sh_rest": leaves["features_rest"], "opacities": leaves["opacities"]}
+
+
+def native_view_forward(D, leaves, rs):
+    """gsr_forward for a leaf dict in either layout (see _sh_and_raw); returns D._forward_native's 9-tuple."""
+    e = torch.empty(0)
+    sh, raw = _sh_and_raw(leaves)
+    return D._forward_native(leaves["means3D"], sh, e, leaves["segments"], leaves["opacities"], leaves["scales"], leaves["rotations"], e, rs,
+                             sh_rest=raw["sh_rest"] if raw else None, raw_params=raw is not None)
+
+
 def shard_views(num_views, rank, world):
     """Indices of the views this rank renders."""
     return list(range(rank, num_views, world))
@@ -152,9 +168,11 @@ def native_view_backward(D, leaves, rs, fwd, upstream, flat, first, means2D_grad
     e = torch.empty(0)
     if means2D_grad is not None and not first:
         means2D_grad.zero_()  # per-view screen-space gradient (densification statistics need each view's own norm)
+    sh, raw = _sh_and_raw(leaves)
     return D._backward_native(rs, leaves["means3D"], radii, e, leaves["segments"], leaves["scales"], leaves["rotations"], e,
-                              upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"), leaves["shs"],
-                              geom, R, binb, img, alpha, out=flat.backward_out(means2D_grad), accumulate=not first)
+                              upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"), sh,
+                              geom, R, binb, img, alpha, out=flat.backward_out(means2D_grad), accumulate=not first,
+                              sh_rest=raw["sh_rest"] if raw else None, raw_params=raw is not None, opacities=raw["opacities"] if raw else None)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -169,10 +187,11 @@ def native_view_backward_packets(D, leaves, rs, fwd, upstream, means2D_grad=None
     capacity (`state["cap"]` of exchange_packets) lets the blob be all-gathered in place, without a repacking copy."""
     R, color, depth, segment, alpha, radii, geom, binb, img = fwd
     nvis = D.last_num_visible()
+    sh, raw = _sh_and_raw(leaves)
     blob, count = D._backward_packets_native(rs, leaves["means3D"], radii, leaves["segments"], leaves["scales"], leaves["rotations"],
                                              upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"),
-                                             leaves["shs"], geom, R, binb, img, alpha, capacity=max(nvis, int(capacity)),
-                                             means2D_grad=means2D_grad)
+                                             sh, geom, R, binb, img, alpha, capacity=max(nvis, int(capacity)),
+                                             means2D_grad=means2D_grad, raw_params=raw)
     return blob, count, nvis
 
 
@@ -262,10 +281,11 @@ class PeerPacketExchange:
         """Backward of this rank's view v of the step, written as a blob into the current peer-visible buffer."""
         R, color, depth, segment, alpha, radii, geom, binb, img = fwd
         base = self.blob_ptr(self.local[self.parity], v)
+        sh, raw = _sh_and_raw(leaves)
         _, count = self.D._backward_packets_native(rs, leaves["means3D"], radii, leaves["segments"], leaves["scales"], leaves["rotations"],
                                                    upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"),
-                                                   leaves["shs"], geom, R, binb, img, alpha, capacity=self.capacity, means2D_grad=means2D_grad,
-                                                   raw=(base + 4 * self.packet_off, base + 4 * self.index_off))
+                                                   sh, geom, R, binb, img, alpha, capacity=self.capacity, means2D_grad=means2D_grad,
+                                                   raw=(base + 4 * self.packet_off, base + 4 * self.index_off), raw_params=raw)
         return count
 
     def exchange(self, flat, leaves, all_campos, sh_degree):

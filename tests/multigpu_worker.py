@@ -61,6 +61,35 @@ for step in range(3):
     dist.broadcast(ref, 0)
     assert torch.equal(ref, peer.buffer), "peer replicas differ"
 px.close()
+# raw-parameter layout end to end: flat parameters -> fused-activation forward -> packets into peer buffers -> gather into the
+# split flat gradient buffer -> fused Adam; replicas must stay bitwise identical after the optimiser step
+optim = importlib.import_module(H.PKG_NAME + ".optim")
+eps_ = 1e-6
+logit = lambda p: torch.log(p.clamp(eps_, 1 - eps_) / (1 - p.clamp(eps_, 1 - eps_)))
+params = optim.FlatParameters.from_tensors({"means3D": gs["means3D"], "features_dc": gs["shs"][:, :1].contiguous(),
+                                            "features_rest": gs["shs"][:, 1:].contiguous(), "segments": logit(gs["segments"]),
+                                            "opacities": logit(gs["opacities"]), "scales": torch.log(gs["scales"]), "rotations": gs["rotations"] * 1.5})
+rgrads = mv.FlatGradients(P, dev, split_sh=True)
+opt = optim.FusedAdam(params, rgrads, {"xyz": 1e-4, "f_dc": 2.5e-3, "f_rest": 1.25e-4, "opacity": 0.05, "segment": 0.01, "scaling": 5e-3, "rotation": 1e-3})
+px2 = mv.PeerPacketExchange(D, dist, P, 1, rank, world, dev)
+# dense raw-parameter reference: each rank's own dense gradient, all-reduced
+fwd_r = mv.native_view_forward(D, params.views, rs)
+dense_r = mv.FlatGradients(P, dev, split_sh=True)
+mv.native_view_backward(D, params.views, rs, fwd_r, ug, dense_r, first=True)
+dense_r.allreduce(dist)
+px2.view_backward(params.views, rs, fwd_r, ug, 0)
+px2.exchange(rgrads, params.views, campos, 3)
+torch.cuda.synchronize()
+err_r = float((rgrads.buffer - dense_r.buffer).abs().max()) / float(dense_r.buffer.abs().max())
+assert err_r <= 2e-5, err_r
+before = params.buffer.clone()
+opt.step()
+torch.cuda.synchronize()
+assert not torch.equal(before, params.buffer)
+ref = params.buffer.clone()
+dist.broadcast(ref, 0)
+assert torch.equal(ref, params.buffer), "parameter replicas differ after the fused Adam step"
+px2.close()
 if rank == 0:
     print("multigpu ok: world=%d rel_err=%.3e" % (world, err))
 dist.destroy_process_group()

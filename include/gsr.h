@@ -206,6 +206,14 @@ typedef struct GsrAdamGroup {
 int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const GsrAdamGroup* groups, int32_t num_groups,
                   double beta1, double beta2, double eps, int32_t step, gsr_stream_t stream);
 
+/* Fused photometric loss of the training step (train.py:110-111 with utils/loss_utils.py:104-150):
+ *   loss = (1 - lambda_dssim) * mean|image - gt| + lambda_dssim * (1 - mean(SSIM_11x11,sigma=1.5(image, gt)))
+ * loss_out[3] = {L1, SSIM, loss} (device); dL_dimage [C,H,W] = grad_scale * dloss/dimage (NULL: forward only). Two launches,
+ * deterministic (no float atomics). image / gt are [C,H,W] fp32; zero padding like F.conv2d(padding=5). */
+size_t gsr_image_loss_scratch_bytes(int32_t C, int32_t H, int32_t W);
+int gsr_image_loss(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, float lambda_dssim, float grad_scale,
+                   float* loss_out, float* dL_dimage, void* scratch, size_t scratch_bytes, gsr_stream_t stream);
+
 /* Number of visible Gaussians of the most recent gsr_forward on the calling thread. */
 uint32_t gsr_last_num_visible(void);
 

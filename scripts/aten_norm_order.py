@@ -1,3 +1,7 @@
+"""How does ATen associate the sum of squares in torch.linalg.vector_norm / F.normalize over a contiguous [P,4] tensor?
+Enumerates every order (sequential and pairwise, with and without fused multiply-add) and counts mismatching bits against
+torch on 10^6 random quaternions. Result on torch 2.11 / B200: (x^2 + z^2) + (y^2 + w^2), products rounded separately -> 0
+mismatches; every other order 7-19 %. csrc/gsr_math.cuh:quat_norm is spelled accordingly (fused-activation entry)."""
 import itertools, torch
 torch.manual_seed(0)
 q = (torch.randn(1_000_000, 4, device="cuda") * 2.0)

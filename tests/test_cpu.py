@@ -152,3 +152,46 @@ def test_oracle_matches_reference_cuda_fixture():
         for k in ["grad_means3D", "grad_means2D", "grad_sh", "grad_segments", "grad_opacities", "grad_scales", "grad_rotations"]:
             a, b = st["grads"][k], z[k].reshape(st["grads"][k].shape)
             assert np.quantile(np.abs(a - b), 0.999) <= 1e-3 * np.abs(b).max(), k
+
+
+def test_flat_buffer_layouts_and_packet_blob_helpers():
+    """Host-side layout logic of the multi-view / optimiser plumbing (no CUDA calls): flat gradient / parameter buffers in both
+    SH layouts, group offsets, and the view-blob geometry used by the packet exchange."""
+    import importlib
+
+    import torch
+
+    import helpers as H
+
+    H.pkg()
+    mv = importlib.import_module(H.PKG_NAME + ".multiview")
+    optim = importlib.import_module(H.PKG_NAME + ".optim")
+    D = importlib.import_module(H.PKG_NAME + ".diff_gaussian_rasterization")
+    P = 37
+    f = mv.FlatGradients(P, "cpu")
+    assert f.buffer.numel() == 61 * P and list(f.views) == ["means3D", "shs", "segments", "opacities", "scales", "rotations"]
+    s = mv.FlatGradients(P, "cpu", split_sh=True)
+    assert s.buffer.numel() == 61 * P and s.views["features_dc"].shape == (P, 1, 3) and s.views["features_rest"].shape == (P, 15, 3)
+    s.views["features_rest"].fill_(2.0)
+    assert float(s.buffer.sum()) == 2.0 * P * 45  # views alias the flat buffer
+    out = s.backward_out()
+    assert out["sh"].data_ptr() == s.views["features_dc"].data_ptr() and out["sh_rest"].data_ptr() == s.views["features_rest"].data_ptr()
+    assert f.backward_out()["sh_rest"] is None
+    fp = optim.FlatParameters.from_tensors({k: torch.full(v.shape, float(i)) for i, (k, v) in enumerate(s.views.items())})
+    offs = fp.offsets()
+    assert [offs[k][0] for k in offs] == [0, 3 * P, 6 * P, 51 * P, 53 * P, 54 * P, 57 * P] and sum(c for _, c in offs.values()) == 61 * P
+    for i, k in enumerate(offs):
+        o, c = offs[k]
+        assert float(fp.buffer[o:o + c].min()) == float(fp.buffer[o:o + c].max()) == float(i)
+    assert mv.sh_coeffs_of(s.views) == 16 and mv.sh_coeffs_of(f.views) == 16
+    assert set(optim.GROUPS.values()) == set(s.views)  # the reference's seven parameter groups
+    # view blobs: index first (2 words per 32 Gaussians, padded to 128 B), then 17-word packets, padded to 128 B
+    for P2 in (1, 32, 33, 30_000):
+        nidx = D.packet_index_words(P2)
+        assert nidx % 32 == 0 and nidx >= 2 * ((P2 + 31) // 32)
+        for cap in (1, 2, 7, 1024):
+            words = D.packet_blob_words(P2, cap)
+            blob = torch.zeros(words, dtype=torch.int32)
+            assert words % 32 == 0 and cap <= D.packet_blob_capacity(blob, P2) <= cap + 2
+            pk, bits, first = D.packet_blob_views(blob, P2)
+            assert pk.shape[1] == 17 and bits.numel() == first.numel() == (P2 + 31) // 32

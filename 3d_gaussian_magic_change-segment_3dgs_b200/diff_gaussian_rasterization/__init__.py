@@ -356,7 +356,12 @@ def gather_packets_v(means3D, campos_all, sh_degree, sh_coeffs, view_ptrs, packe
 
 
 def peer_alloc(nbytes, device):
-    """gsr_peer_alloc on `device`: (device address, 64-byte handle as bytes)."""
+    """gsr_peer_alloc on `device`: (device address, 64-byte handle as bytes). GSR_PEER_DISABLE=1 makes it fail (to exercise
+    the callers' fallback to the NCCL exchange on nodes without CUDA IPC)."""
+    import os
+
+    if os.environ.get("GSR_PEER_DISABLE"):
+        raise RuntimeError("peer buffers disabled by GSR_PEER_DISABLE")
     L = _lib.lib()
     with torch.cuda.device(device):
         ptr = ctypes.c_void_p()

@@ -245,34 +245,73 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
 # packets straight over NVLink while it sums them -- the transfer IS the kernel's loads: no all-gather, no staging copy, no
 # host read. Blobs are double-buffered: a rank may start writing step s+1 while a slower rank still reads step s.
 # ---------------------------------------------------------------------------------------------------------------------
+class PeerUnavailable(RuntimeError):
+    """Raised on EVERY rank when peer-visible buffers could not be set up on some rank (no CUDA IPC / no peer access)."""
+
+
 class PeerPacketExchange:
     def __init__(self, D, dist, P, views_per_rank, rank, world, device, capacity=None, group=None):
+        """Collective: all ranks construct it together. Either every rank succeeds or every rank raises PeerUnavailable (the
+        outcome is agreed with an all-reduce), so callers can fall back to exchange_packets (NCCL all-gather) consistently."""
         self.D, self.dist, self.P, self.nv, self.rank, self.world, self.device, self.group = D, dist, P, views_per_rank, rank, world, device, group
         self.capacity = int(capacity) if capacity else P  # packets per view; P always fits
         self.index_off = 0
         self.packet_off = D.packet_index_words(P)  # 128-byte aligned
         self.blob_words = D.packet_blob_words(P, self.capacity)
         nbytes = 4 * self.blob_words * self.nv
-        self.local, self.peers, handles = [], [], []
-        for b in range(2):
-            ptr, h = D.peer_alloc(nbytes, device)
-            self.local.append(ptr)
-            handles.append(h)
-        mine = torch.tensor(list(handles[0] + handles[1]), dtype=torch.uint8, device=device)
+        self.local, self.peers, handles = [], [[], []], []
+        self._opened = False
+        err = None
+        try:
+            for b in range(2):
+                ptr, h = D.peer_alloc(nbytes, device)
+                self.local.append(ptr)
+                handles.append(h)
+        except Exception as ex:  # reported collectively below
+            err = ex
+            handles = [bytes(64), bytes(64)]
+        mine = torch.tensor(list(handles[0] + handles[1]) + [0 if err else 1], dtype=torch.uint8, device=device)
         everyone = torch.empty(world * mine.numel(), dtype=torch.uint8, device=device)
         if world > 1:
             dist.all_gather_into_tensor(everyone, mine, group=group)
         else:
             everyone.copy_(mine)
-        everyone = everyone.cpu().view(world, 2, -1)
-        for b in range(2):
-            row = []
-            for r in range(world):
-                row.append(self.local[b] if r == rank else D.peer_open(bytes(everyone[r, b].tolist()), device))
-            self.peers.append(row)
+        everyone = everyone.cpu().view(world, -1)
+        if bool((everyone[:, -1] == 1).all()):
+            try:
+                for b in range(2):
+                    for r in range(world):
+                        h = bytes(everyone[r, 64 * b:64 * (b + 1)].tolist())
+                        self.peers[b].append(self.local[b] if r == rank else D.peer_open(h, device))
+            except Exception as ex:
+                err = ex
+        elif err is None:
+            err = RuntimeError("another rank could not allocate its peer buffer")
+        ok = torch.tensor([0.0 if err else 1.0], device=device)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if float(ok.item()) < 1.0:
+            self._release()
+            raise PeerUnavailable("peer-memory exchange unavailable on this node: %s" % (err or "failed on another rank"))
         self.parity = 0
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
         self._opened = True
+
+    def _release(self):
+        for b in range(2):
+            for r, ptr in enumerate(self.peers[b]):
+                if r != self.rank:
+                    try:
+                        self.D.peer_close(ptr, self.device)
+                    except Exception:
+                        pass
+        self.peers = [[], []]
+        for ptr in self.local:
+            try:
+                self.D.peer_free(ptr, self.device)
+            except Exception:
+                pass
+        self.local = []
 
     def blob_ptr(self, base, v):
         return base + 4 * self.blob_words * v
@@ -300,6 +339,7 @@ class PeerPacketExchange:
         self.parity ^= 1
 
     def close(self):
+        """Collective. Unmap the peers' buffers, then (after a barrier) free this rank's."""
         if not getattr(self, "_opened", False):
             return
         self._opened = False
@@ -307,10 +347,12 @@ class PeerPacketExchange:
         if self.world > 1:
             self.dist.barrier(group=self.group)
         for b in range(2):
-            for r in range(self.world):
+            for r, ptr in enumerate(self.peers[b]):
                 if r != self.rank:
-                    self.D.peer_close(self.peers[b][r], self.device)
+                    self.D.peer_close(ptr, self.device)
+        self.peers = [[], []]
         if self.world > 1:
             self.dist.barrier(group=self.group)
-        for b in range(2):
-            self.D.peer_free(self.local[b], self.device)
+        for ptr in self.local:
+            self.D.peer_free(ptr, self.device)
+        self.local = []

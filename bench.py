@@ -273,7 +273,14 @@ def main():
 
     use_packets = use_flat and dist is not None and args.grad_exchange == "packets"
     use_peer = use_flat and dist is not None and args.grad_exchange == "peer"
-    px = mv.PeerPacketExchange(Dmod, dist, P, V, rank, nranks, device) if use_peer else None
+    px = None
+    if use_peer:
+        try:
+            px = mv.PeerPacketExchange(Dmod, dist, P, V, rank, nranks, device)
+        except mv.PeerUnavailable as ex:  # raised on every rank together: fall back to the NCCL all-gather of the same packets
+            if rank == 0:
+                print("bench: %s -- falling back to --grad-exchange packets" % ex, file=sys.stderr, flush=True)
+            use_peer, use_packets = False, True
     all_campos = None
     if use_packets or use_peer:  # every rank knows every camera of the step
         all_campos = [[syn.make_camera(W, Hh, yaw_deg=45.0 * (r * V + v))["campos"].to(device) for v in range(V)] for r in range(nranks)]

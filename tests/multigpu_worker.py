@@ -90,6 +90,15 @@ ref = params.buffer.clone()
 dist.broadcast(ref, 0)
 assert torch.equal(ref, params.buffer), "parameter replicas differ after the fused Adam step"
 px2.close()
+# a rank that cannot set up peer buffers makes EVERY rank raise PeerUnavailable (no hang, no half-open state)
+if rank == world - 1:
+    os.environ["GSR_PEER_DISABLE"] = "1"
+try:
+    mv.PeerPacketExchange(D, dist, P, 1, rank, world, dev)
+    raise AssertionError("expected PeerUnavailable")
+except mv.PeerUnavailable:
+    pass
+os.environ.pop("GSR_PEER_DISABLE", None)
 if rank == 0:
     print("multigpu ok: world=%d rel_err=%.3e" % (world, err))
 dist.destroy_process_group()

@@ -29,7 +29,6 @@ __global__ void __launch_bounds__(PRE_BLOCK) depth_keys_kernel(GeomState g, uint
     const float depth = g.rec[3 * (size_t)slot + 2].y;
     keys[dst] = __float_as_uint(depth);
     vals[dst] = slot;
-    g.vis_slot[dst] = slot; // kept for the backward's dense pass over visible Gaussians
 }
 
 // (3a) tiles_touched of the Gaussians in depth order

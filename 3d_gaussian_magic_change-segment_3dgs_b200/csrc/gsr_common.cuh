@@ -32,7 +32,6 @@ struct GeomState
     ushort4* rect;       // [slots] tile rectangle {xmin, ymin, xmax, ymax} (auxiliary.h:46-56)
     uint32_t* slot_gid;  // [slots] Gaussian id of the slot
     uint8_t* clamped;    // [slots] bit c set <=> SH colour channel c was clamped (forward.cu:67-69)
-    uint32_t* vis_slot;  // [slots] slot of the r-th visible Gaussian (Gaussian-id order), r < V
     uint32_t* blk_count; // [nblk] visible Gaussians per slot-block
     uint32_t* blk_offset;// [nblk] exclusive scan of blk_count
     uint32_t* dkeys[2];  // [slots] depth bits of the visible Gaussians (ping-pong), first V used
@@ -83,7 +82,6 @@ inline size_t geom_layout(char* base, int P, GeomState& g)
     carve(p, g.rect, (size_t)g.slots);
     carve(p, g.slot_gid, (size_t)g.slots);
     carve(p, g.clamped, (size_t)g.slots);
-    carve(p, g.vis_slot, (size_t)g.slots);
     carve(p, g.blk_count, (size_t)g.nblk);
     carve(p, g.blk_offset, (size_t)g.nblk + 1);
     for (int i = 0; i < 2; i++) {
@@ -196,6 +194,7 @@ struct PreBwdArgs
     uint32_t packet_capacity;
     uint32_t* packet_count;
     uint32_t* vis_index;
+    int fill; // set by launch_preprocess_bwd: dense mode, the kernel zero-fills the rows its CTA owns
 };
 
 struct GatherPacketsArgs

@@ -192,26 +192,18 @@ __global__ void __launch_bounds__(1024) block_offsets_kernel(GeomState g)
 // ------------------------------------------------------------------------------------------------ backward
 // One thread per VISIBLE Gaussian (rank r in Gaussian-id order -> slot -> id): the heavy chain rule runs on dense warps
 // (only ~20% of the Gaussians of a view are visible; a thread-per-Gaussian layout would execute it with ~80% idle lanes).
-constexpr int BWD_THREADS = 128;
+constexpr int BWD_THREADS = 64; // a 256-Gaussian block has ~50 visible ones at 20 % visibility: two dense warps
 constexpr int SH_ROW_STRIDE = 49; // 48 floats + 1: lane rows start in different banks
 
-__global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBwdArgs a)
+// The whole chain rule of one visible Gaussian (backward.cu:144-412 = K8 + K9, plus the fused activations' backward). Called by a
+// full warp: `visible` marks the lanes that carry a Gaussian, `nrows` (warp-uniform) is how many of the warp's lanes do, `r` is the
+// Gaussian's rank among the visible ones (= its packet index), s_sh_warp the warp's 32 x SH_ROW_STRIDE staging rows.
+__device__ __forceinline__ void preprocess_bwd_one(const PreBwdArgs& a, const bool visible, const uint32_t slot, const uint32_t r,
+                                                   const uint32_t nrows, const uint32_t lane, float* s_sh_warp, const float* s_view,
+                                                   const float* s_proj)
 {
-    __shared__ float s_view[16], s_proj[16];
-    __shared__ float s_sh[BWD_THREADS / 32][32 * SH_ROW_STRIDE]; // per warp: 32 SH gradient rows, transposed out below
-    if (threadIdx.x < 16) {
-        s_view[threadIdx.x] = a.view[threadIdx.x];
-        s_proj[threadIdx.x] = a.proj[threadIdx.x];
-    }
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * BWD_THREADS + threadIdx.x;
-    const uint32_t V = a.g.counters[CNT_VISIBLE];
-    if ((r & ~31u) >= V) return; // whole warp past the end
-    const bool visible = r < V;
-    const uint32_t slot = visible ? a.g.vis_slot[r] : 0u;
     const int idx = visible ? (int)a.g.slot_gid[slot] : 0;
-    float* my_sh = &s_sh[warp][lane * SH_ROW_STRIDE];
+    float* my_sh = s_sh_warp + lane * SH_ROW_STRIDE;
 
     float3 dL_dmean = {0.f, 0.f, 0.f};
     float2 dL_dmean2D = {0.f, 0.f};
@@ -376,7 +368,6 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
     //      touch 32 different rows per store instruction, half a sector each) ----
     if (a.packets) {
         // ---- packet mode: 17 words per visible Gaussian; the receiver rebuilds the SH rows from the colour gradient ----
-        if (r == 0) *a.packet_count = V;
         if (visible && r < a.packet_capacity) {
             float3 dRGB = dL_dcolor;
             if (a.shs != nullptr) { // the clamp mask of sh_backward (backward.cu:31-34)
@@ -408,10 +399,9 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
     if (a.out.dL_dsh) {
         __syncwarp();
         const int row_floats = a.M * 3;
-        const uint32_t nrows = min(32u, V - (r & ~31u));
         for (uint32_t rr = 0; rr < nrows; rr++) {
             const int id_rr = __shfl_sync(0xffffffffu, idx, rr);
-            const float* src = &s_sh[warp][rr * SH_ROW_STRIDE];
+            const float* src = s_sh_warp + rr * SH_ROW_STRIDE;
             if (a.out.dL_dsh_rest) { // raw-parameter mode: coefficient 0 -> features_dc row, the rest -> features_rest row
                 float* dc = a.out.dL_dsh + (size_t)id_rr * 3;
                 float* rest = a.out.dL_dsh_rest + (size_t)id_rr * (row_floats - 3) - 3;
@@ -473,6 +463,48 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
     if (a.out.dL_dcov3D) {
 #pragma unroll
         for (int k = 0; k < 6; k++) put(a.out.dL_dcov3D + 6 * i + k, dL_dcov3D[k]);
+    }
+}
+
+// Dense / accumulate / packet backward over the visible Gaussians, one CTA per 256-Gaussian preprocess block. The forward's slot
+// layout makes that block's visible Gaussians the contiguous slots [256 b, 256 b + blk_count[b]), so there is no index list to
+// chase, and the CTA OWNS the gradient rows of Gaussians [256 b, 256 b + 256): in dense mode it first zero-fills them (coalesced
+// 16-byte stores) and then overwrites the visible ones, which still sit in L2 -- the API's "dense rows, zeros for invisible
+// Gaussians" costs no separate 1.5 GB memset pass and nothing competes with the compositing backward for HBM.
+__global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBwdArgs a)
+{
+    __shared__ float s_view[16], s_proj[16];
+    __shared__ float s_sh[BWD_THREADS / 32][32 * SH_ROW_STRIDE]; // per warp: 32 SH gradient rows, transposed out by the body
+    if (threadIdx.x < 16) {
+        s_view[threadIdx.x] = a.view[threadIdx.x];
+        s_proj[threadIdx.x] = a.proj[threadIdx.x];
+    }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x;
+    const uint32_t cnt = a.g.blk_count[b], base = a.g.blk_offset[b];
+    if (a.fill) { // dense mode: this CTA's 256 rows of every output tensor
+        const size_t lo = (size_t)b * PRE_BLOCK, hi = min((size_t)a.P, lo + PRE_BLOCK);
+        const int Mdc = a.out.dL_dsh_rest ? 1 : a.M;
+        const struct { float* p; int row; } t[10] = {
+            {a.out.dL_dsh, Mdc * 3}, {a.out.dL_dsh_rest, (a.M - 1) * 3}, {a.out.dL_dmeans3D, 3}, {a.out.dL_dmeans2D, 3}, {a.out.dL_dopacity, 1},
+            {a.out.dL_dcolors, 3}, {a.out.dL_dsegments, a.S > 0 ? a.S : 0}, {a.out.dL_dscales, 3}, {a.out.dL_drotations, 4}, {a.out.dL_dcov3D, 6}};
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            if (!t[k].p || t[k].row <= 0) continue;
+            float* dst = t[k].p + lo * t[k].row; // 256 * row * 4 bytes per block: always 16-byte aligned
+            const size_t n = (hi - lo) * t[k].row, n4 = n >> 2;
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (size_t i = threadIdx.x; i < n4; i += BWD_THREADS) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (size_t i = (n4 << 2) + threadIdx.x; i < n; i += BWD_THREADS) dst[i] = 0.f;
+        }
+    }
+    if (a.packets && b == 0 && threadIdx.x == 0) *a.packet_count = a.g.counters[CNT_VISIBLE];
+    __syncthreads(); // view matrices staged; zero rows ordered before this CTA's visible rows
+    for (uint32_t j0 = 0; j0 < cnt; j0 += BWD_THREADS) {
+        const uint32_t j = j0 + threadIdx.x;
+        if ((j & ~31u) >= cnt) continue; // whole warp past the end
+        __syncwarp();                    // the previous trip's row transposition is done with the staging rows
+        preprocess_bwd_one(a, j < cnt, b * PRE_BLOCK + min(j, cnt - 1), base + j, min(32u, cnt - (j & ~31u)), lane, s_sh[warp], s_view, s_proj);
     }
 }
 
@@ -750,26 +782,31 @@ int launch_block_offsets(const GeomState& g, cudaStream_t s)
     block_offsets_kernel<<<1, 1024, 0, s>>>(g); count_launches(1);
     return 0;
 }
-// Dense gradient tensors are an API requirement (zeros for invisible Gaussians). Whole-tensor fills run at the HBM write peak
-// (measured 7.5 TB/s on B200, vs 3.3 TB/s for a kernel that skips the scattered rows of visible Gaussians); the dense pass then
-// overwrites the ~20% visible rows. The fills do not depend on the compositing backward, so the caller runs them on a side
-// stream while that (issue-bound) kernel executes.
+// Dense gradient tensors are an API requirement (zeros for invisible Gaussians). Two ways, A/B with GSR_FILL_MODE:
+//   memset (default): whole-tensor cudaMemsetAsync fills (7.5 TB/s) that the caller runs on a side stream while the issue-bound
+//                     compositing backward executes; the dense pass then overwrites the ~20 % visible rows;
+//   kernel:           every CTA of preprocess_bwd_kernel zero-fills the 256 rows it owns before writing its visible rows.
+static bool fill_in_kernel()
+{
+    static const bool v = getenv("GSR_FILL_MODE") && !strcmp(getenv("GSR_FILL_MODE"), "kernel");
+    return v;
+}
 int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
     const size_t P = (size_t)a.P;
+    const int Mdc = a.out.dL_dsh_rest ? 1 : a.M;
     struct { float* p; size_t floats; } fills[] = {
-        {a.out.dL_dsh, a.out.dL_dsh_rest ? P * 3 : P * (size_t)a.M * 3},
-        {a.out.dL_dsh_rest, P * (size_t)(a.M > 1 ? a.M - 1 : 0) * 3}, {a.out.dL_dmeans3D, P * 3}, {a.out.dL_dmeans2D, P * 3}, {a.out.dL_dopacity, P},
-        {a.out.dL_dcolors, P * 3}, {a.out.dL_dsegments, P * (size_t)(a.S > 0 ? a.S : 0)}, {a.out.dL_dscales, P * 3},
-        {a.out.dL_drotations, P * 4}, {a.out.dL_dcov3D, P * 6}};
+        {a.out.dL_dsh, P * (size_t)Mdc * 3}, {a.out.dL_dsh_rest, P * (size_t)(a.M > 1 ? a.M - 1 : 0) * 3}, {a.out.dL_dmeans3D, P * 3},
+        {a.out.dL_dmeans2D, P * 3}, {a.out.dL_dopacity, P}, {a.out.dL_dcolors, P * 3}, {a.out.dL_dsegments, P * (size_t)(a.S > 0 ? a.S : 0)},
+        {a.out.dL_dscales, P * 3}, {a.out.dL_drotations, P * 4}, {a.out.dL_dcov3D, P * 6}};
     if (a.packets) {
         if (a.out.dL_dmeans2D) GSR_CUDA(cudaMemsetAsync(a.out.dL_dmeans2D, 0, P * 3 * sizeof(float), s));
         if (a.vis_index) {
             const size_t W = (P + 31) / 32;
             GSR_CUDA(cudaMemsetAsync(a.vis_index, 0, 2 * W * sizeof(uint32_t), s));
         }
-    } else if (!a.out.accumulate) {
+    } else if (!a.out.accumulate && !fill_in_kernel()) {
         for (auto& f : fills)
             if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
     }
@@ -779,8 +816,9 @@ int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
 int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
-    const uint32_t nb = (a.g.slots + BWD_THREADS - 1) / BWD_THREADS; // capacity: V is only known on the device here
-    preprocess_bwd_kernel<<<nb, BWD_THREADS, 0, s>>>(a); count_launches(1);
+    PreBwdArgs b = a;
+    b.fill = (!a.packets && !a.out.accumulate && fill_in_kernel()) ? 1 : 0;
+    preprocess_bwd_kernel<<<a.g.nblk, BWD_THREADS, 0, s>>>(b); count_launches(1);
     return 0;
 }
 int launch_apply_packets(const ApplyPacketsArgs& a, cudaStream_t s)

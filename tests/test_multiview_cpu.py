@@ -42,8 +42,10 @@ def _worker(rank, world, port, q):
     leaves = {k: v.clone().requires_grad_(True) for k, v in leaves.items()}
     stats = mv.DensificationStats(leaves["means3D"].shape[0], "cpu")
     total = mv.multiview_step(leaves, cams, _toy_render, _loss, rank=rank, world=world, dist=dist, stats=stats)
-    q.put((rank, float(total), {k: v.grad.clone() for k, v in leaves.items()}, stats.xyz_gradient_accum.clone(), stats.denom.clone(),
-           stats.max_radii2D.clone()))
+    # numpy arrays travel through the queue BY VALUE; torch tensors would be shared through a file-descriptor socket of this
+    # process, which may already be gone when the parent reads the queue (FileNotFoundError, seen 1 run in 3)
+    q.put((rank, float(total), {k: v.grad.numpy().copy() for k, v in leaves.items()}, stats.xyz_gradient_accum.numpy().copy(),
+           stats.denom.numpy().copy(), stats.max_radii2D.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -72,6 +74,8 @@ def test_multiview_step_world2_matches_sequential():
     for p in procs:
         p.join(timeout=180)
         assert p.exitcode == 0, p.exitcode
+    results = [(r, t, {k: torch.from_numpy(v) for k, v in g.items()}, torch.from_numpy(a), torch.from_numpy(d), torch.from_numpy(m))
+               for r, t, g, a, d, m in results]
     for rank, total, grads, acc, den, mr in results:
         assert abs(total - float(stotal)) <= 1e-4 * abs(float(stotal))
         for k in grads:

@@ -627,12 +627,23 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
     static_assert(GATHER_CAP * GSR_PACKET_WORDS <= 32 * SH_ROW_STRIDE, "staging must fit");
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < a.num_views * 3; i += GATHER_THREADS) s_cam[i] = a.campos[i];
-    const uint32_t id = blockIdx.x * GATHER_THREADS + threadIdx.x;
-    const bool valid = id < (uint32_t)a.P;
-    const uint32_t W = ((uint32_t)a.P + 31u) >> 5, word_i = min(id >> 5, W - 1);
+    __syncthreads();
+    const uint32_t W = ((uint32_t)a.P + 31u) >> 5; // groups of 32 Gaussians = index pairs per view
     const uint32_t lt_mask = (1u << lane) - 1u;
     const bool want_sh = a.out.dL_dsh && a.M > 0;
     uint32_t* stage = s_buf[warp];
+    const uint32_t nvg0 = (uint32_t)min(GATHER_GROUP, a.num_views);
+    // Persistent warps: warp w takes groups w, w + (warps in the grid), ... The index pairs of the NEXT group are requested before
+    // the current one is processed, so the (possibly remote) index round trip is off the critical path of every group but the first.
+    const uint32_t warps_total = gridDim.x * (GATHER_THREADS / 32);
+    uint32_t grp = blockIdx.x * (GATHER_THREADS / 32) + warp;
+    uint2 pr_next = make_uint2(0u, 0u);
+    if (grp < W && lane < nvg0) pr_next = __ldg(reinterpret_cast<const uint2*>(a.views[lane] + a.index_off) + grp);
+    for (; grp < W; grp += warps_total) {
+    const uint2 pr_first = pr_next;
+    if (grp + warps_total < W && lane < nvg0) pr_next = __ldg(reinterpret_cast<const uint2*>(a.views[lane] + a.index_off) + grp + warps_total);
+    const uint32_t id = grp * 32u + lane, word_i = grp;
+    const bool valid = id < (uint32_t)a.P;
     float acc[13], dsh[48];
 #pragma unroll
     for (int k = 0; k < 13; k++) acc[k] = 0.f;
@@ -640,12 +651,11 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
     for (int k = 0; k < 48; k++) dsh[k] = 0.f;
     const size_t i = (size_t)(valid ? id : 0);
     const float3 pos = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
-    __syncthreads();
     for (int g0 = 0; g0 < a.num_views; g0 += GATHER_GROUP) {
         const uint32_t nvg = (uint32_t)min(GATHER_GROUP, a.num_views - g0);
         uint32_t my_bits = 0u, my_first = 0u;
         if (lane < nvg) {
-            const uint2 pr = __ldg(reinterpret_cast<const uint2*>(a.views[g0 + lane] + a.index_off) + word_i);
+            const uint2 pr = g0 == 0 ? pr_first : __ldg(reinterpret_cast<const uint2*>(a.views[g0 + lane] + a.index_off) + word_i);
             const uint32_t cnt = __popc(pr.x), f0 = ~pr.y;
             const bool ok = f0 <= a.capacity && cnt <= a.capacity - f0; // a corrupt index cannot make a span leave its blob
             my_bits = ok ? pr.x : 0u;
@@ -733,7 +743,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
 #pragma unroll
         for (int k = 0; k < 48; k++) my[k] = dsh[k];
         __syncwarp();
-        const uint32_t first_row = blockIdx.x * GATHER_THREADS + warp * 32;
+        const uint32_t first_row = grp * 32u;
         if (first_row < (uint32_t)a.P) {
             const uint32_t nrows = min(32u, (uint32_t)a.P - first_row);
             const int row_floats = a.M * 3;
@@ -758,6 +768,8 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
             }
         }
     }
+    __syncwarp(); // the row store is done with the staging buffer before the next group stages into it
+    } // groups
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -830,7 +842,15 @@ int launch_apply_packets(const ApplyPacketsArgs& a, cudaStream_t s)
 int launch_gather_packets(const GatherPacketsArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
-    gather_packets_kernel<<<(a.P + GATHER_THREADS - 1) / GATHER_THREADS, GATHER_THREADS, 0, s>>>(a); count_launches(1);
+    static int resident = 0; // persistent grid: 4 CTAs per SM (launch bounds), fewer when there is less work
+    if (!resident) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident = 4 * (sms > 0 ? sms : 148);
+    }
+    const unsigned groups = ((unsigned)a.P + 31u) / 32u, want = (groups + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32);
+    gather_packets_kernel<<<want < (unsigned)resident ? want : (unsigned)resident, GATHER_THREADS, 0, s>>>(a); count_launches(1);
     return 0;
 }
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s)

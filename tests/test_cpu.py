@@ -195,3 +195,17 @@ def test_flat_buffer_layouts_and_packet_blob_helpers():
             assert words % 32 == 0 and cap <= D.packet_blob_capacity(blob, P2) <= cap + 2
             pk, bits, first = D.packet_blob_views(blob, P2)
             assert pk.shape[1] == 17 and bits.numel() == first.numel() == (P2 + 31) // 32
+
+
+def test_graft_entry_build_runs():
+    """The driver's "does it build" check: __graft_entry__.build() must succeed on a machine without a GPU (everything is
+    cached after the first build, so this is a few seconds)."""
+    import importlib
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
+    assert callable(entry.smoke)

@@ -5,10 +5,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of views: for each of the rank's views, rasterize_gaussians forward
-(colour + depth + alpha + segment) and backward (all parameter gradients, dense), through the drop-in PyTorch API; at
-N > 1 the gradients of the replicated Gaussians are then summed with NCCL all-reduces (multi-view data parallelism,
-SURVEY.md 8e). Workload = BASELINE.json configs[2] ("cfg3": 6M Gaussians SH3, 1920x1080, depth render + depth gradient),
-the configuration the headline metric is quoted on; synthetic seeded scene (synthetic.py).
+(colour + depth + alpha + segment) and backward (all parameter gradients, dense). N = 1: through the drop-in PyTorch API and
+autograd. N > 1 (multi-view data parallelism; parameters replicated, one view per rank per step): the
+gradients of all ranks' views are summed into one flat buffer on every rank -- `--grad-exchange peer` (default): each view's
+backward writes 68-byte packets of its visible Gaussians into peer-visible memory and ONE kernel per rank pulls all ranks'
+packets over NVLink while summing them (multiview.PeerPacketExchange); `packets`: the same packets through one NCCL
+all-gather; `dense`: one NCCL all-reduce of the flat buffer. Workload = BASELINE.json configs[2] ("cfg3": 6M Gaussians SH3,
+1920x1080, depth render + depth gradient), the configuration the headline metric is quoted on; synthetic seeded scene
+(synthetic.py).
 
 Printed JSON (rank 0, one line): `value` = views/s with everything resident in HBM (CUDA events, max over ranks);
 `e2e` = the same step driven from HOST buffers: camera matrices + ground-truth image and depth copied H2D from pinned

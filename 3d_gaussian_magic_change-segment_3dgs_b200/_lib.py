@@ -65,7 +65,7 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
            "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
-           "gsr_peer_free", "gsr_adam_step", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible"]
+           "gsr_peer_free", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible"]
 GSR_ABI_VERSION = 2  # include/gsr.h
 GSR_PACKET_WORDS = 17
 GSR_PEER_HANDLE_BYTES = 64
@@ -122,6 +122,9 @@ def lib():
     L.gsr_image_loss.restype = ctypes.c_int
     L.gsr_image_loss.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.gsr_select_rows.restype = ctypes.c_int
+    L.gsr_select_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                  ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_void_p]
     L.gsr_adam_step.restype = ctypes.c_int
     L.gsr_adam_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GsrAdamGroup), ctypes.c_int32,
                                 ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_void_p]

@@ -145,3 +145,84 @@ extern "C" int gsr_adam_step(float* params, const float* grads, float* exp_avg, 
     adam_kernel<ADAM_TRIPS, false><<<nb, ADAM_THREADS, 0, s>>>(a); count_launches(1);
     return after_launch((cudaStream_t)stream_, false, "adam");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row selection over a flat multi-tensor buffer: densify / prune as ONE index list.
+// The reference rebuilds every parameter and both Adam moments with boolean masks and torch.cat, tensor by tensor
+// (scene/gaussian_model.py:377-441: _prune_optimizer, cat_tensors_to_optimizer -- 2 cats + 2 masks x 7 tensors x 3 states per
+// densification). Here the new row j of every block is row index[j] of the old buffer (-1: a fresh row of zeros, which is what
+// the reference gives the moments of cloned / split Gaussians), for all blocks of the flat buffer in one launch.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace gsr
+{
+namespace
+{
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_CHUNK = SEL_THREADS * 16; // output floats per CTA
+constexpr int SEL_MAX_BLOCKS = 16;
+
+struct SelectArgs
+{
+    const float* src;
+    float* dst;
+    const long long* index;
+    long long n_out, n_src;
+    int num_blocks;
+    int row[SEL_MAX_BLOCKS];                          // floats per row of block k
+    unsigned long long src_off[SEL_MAX_BLOCKS];       // start of block k in src / dst (floats)
+    unsigned long long dst_off[SEL_MAX_BLOCKS];
+    unsigned int first_chunk[SEL_MAX_BLOCKS + 1];
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) select_rows_kernel(const SelectArgs a)
+{
+    int k = 0;
+#pragma unroll 1
+    while (k + 1 < a.num_blocks && blockIdx.x >= a.first_chunk[k + 1]) k++;
+    const unsigned rf = (unsigned)a.row[k];
+    const unsigned long long n = (unsigned long long)a.n_out * rf;
+    const unsigned long long c0 = (unsigned long long)(blockIdx.x - a.first_chunk[k]) * SEL_CHUNK;
+    const float* src = a.src + a.src_off[k];
+    float* dst = a.dst + a.dst_off[k];
+#pragma unroll 4
+    for (int t = 0; t < SEL_CHUNK / SEL_THREADS; t++) {
+        const unsigned long long e = c0 + (unsigned long long)t * SEL_THREADS + threadIdx.x;
+        if (e >= n) break;
+        const unsigned long long r = e / rf;
+        const unsigned c = (unsigned)(e - r * rf);
+        const long long s = a.index[r];
+        dst[e] = (s >= 0 && s < a.n_src) ? src[(unsigned long long)s * rf + c] : 0.f;
+    }
+}
+} // namespace
+} // namespace gsr
+
+extern "C" int gsr_select_rows(const float* src, float* dst, const int64_t* index, int64_t n_out, int64_t n_src, const int32_t* row_floats,
+                               int32_t num_blocks, gsr_stream_t stream_)
+{
+    if (n_out <= 0 || num_blocks <= 0) return 0;
+    if (!src || !dst || !index || !row_floats || num_blocks > SEL_MAX_BLOCKS || n_src < 0) {
+        set_error("gsr_select_rows: invalid argument (1 <= num_blocks <= %d)", SEL_MAX_BLOCKS);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    SelectArgs a;
+    a.src = src; a.dst = dst; a.index = (const long long*)index; a.n_out = n_out; a.n_src = n_src; a.num_blocks = num_blocks;
+    unsigned long long so = 0, dof = 0, chunks = 0;
+    for (int k = 0; k < num_blocks; k++) {
+        if (row_floats[k] <= 0) {
+            set_error("gsr_select_rows: row_floats[%d] must be positive", k);
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+        a.row[k] = row_floats[k]; a.src_off[k] = so; a.dst_off[k] = dof; a.first_chunk[k] = (unsigned int)chunks;
+        so += (unsigned long long)row_floats[k] * (unsigned long long)n_src;
+        dof += (unsigned long long)row_floats[k] * (unsigned long long)n_out;
+        chunks += ((unsigned long long)row_floats[k] * (unsigned long long)n_out + SEL_CHUNK - 1) / SEL_CHUNK;
+    }
+    a.first_chunk[num_blocks] = (unsigned int)chunks;
+    if (chunks > 0x7fffffffull) {
+        set_error("gsr_select_rows: too many rows");
+        return GSR_ERR_UNSUPPORTED;
+    }
+    select_rows_kernel<<<(unsigned int)chunks, SEL_THREADS, 0, (cudaStream_t)stream_>>>(a); count_launches(1);
+    return after_launch((cudaStream_t)stream_, false, "select_rows");
+}

@@ -80,3 +80,117 @@ class FusedAdam:
                                  self.exp_avg_sq.data_ptr(), arr, len(names), self.betas[0], self.betas[1], self.eps, self.step_count,
                                  torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "gsr_adam_step")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Densify / prune as ONE index list
+# ---------------------------------------------------------------------------------------------------------------------
+def select_rows(flat, index):
+    """New flat buffer (same class and block layout as `flat`) whose row j is row index[j] of `flat` in every block;
+    index[j] == -1 gives a row of zeros. index: int64 CUDA tensor. One launch (gsr_select_rows)."""
+    if not flat.buffer.is_cuda:
+        raise RuntimeError("select_rows needs CUDA buffers; libgsr has no CPU path")
+    L = _lib.lib()
+    dev = flat.buffer.device
+    n_out, n_src = int(index.numel()), int(flat.shapes["means3D"][0])
+    idx = index.to(device=dev, dtype=torch.int64).contiguous()
+    sh_coeffs = (flat.shapes["features_rest"][1] + 1) if flat.split_sh else flat.shapes["shs"][1]
+    num_class = flat.shapes["segments"][1]
+    if isinstance(flat, FlatParameters):
+        out = FlatParameters(n_out, dev, sh_coeffs=sh_coeffs, num_class=num_class)
+    else:
+        out = FlatGradients(n_out, dev, sh_coeffs=sh_coeffs, num_class=num_class, split_sh=flat.split_sh)
+    rows = [int(torch.Size(s[1:]).numel()) for s in flat.shapes.values()]
+    arr = (ctypes.c_int32 * len(rows))(*rows)
+    with torch.cuda.device(dev):
+        rc = L.gsr_select_rows(flat.buffer.data_ptr(), out.buffer.data_ptr(), idx.data_ptr(), n_out, n_src, arr, len(rows),
+                               torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "gsr_select_rows")
+    return out
+
+
+def build_rotation(r):
+    """utils/general_utils.py:86-107 (normalised quaternion -> rotation matrix), same expressions."""
+    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+    q = r / norm[:, None]
+    R = torch.zeros((q.size(0), 3, 3), device=r.device)
+    r_, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - r_ * z)
+    R[:, 0, 2] = 2 * (x * z + r_ * y)
+    R[:, 1, 0] = 2 * (x * y + r_ * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - r_ * x)
+    R[:, 2, 0] = 2 * (x * z - r_ * y)
+    R[:, 2, 1] = 2 * (y * z + r_ * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def densify_and_prune(params, opt, xyz_gradient_accum, denom, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, N=2):
+    """GaussianModel.densify_and_prune (scene/gaussian_model.py:500-515: clone, split, prune) on the flat buffers.
+
+    The masks and the handful of new rows (sampled positions, shrunk scales of split Gaussians) are computed with the same torch
+    expressions as the reference on the small selected subsets -- including the one torch.normal call, so the same RNG state
+    gives the same samples -- but the seven parameter tensors and their two Adam moments are rebuilt by ONE row selection each
+    (gsr_select_rows) from a composed index list instead of 2 torch.cat + 2 boolean masks per tensor and state.
+    Returns (new FlatParameters, new FlatGradients, index) and re-targets `opt` (moments reindexed, fresh rows zero); the caller
+    resets its densification statistics to zeros of the new size, as densification_postfix does (:443-463). Like the reference,
+    the screen-size criterion sees max_radii2D AFTER that reset (all zeros), so only the world-size criterion can fire."""
+    v = params.views
+    dev = params.buffer.device
+    P = v["means3D"].size(0)
+    with torch.no_grad():
+        grads = xyz_gradient_accum / denom
+        grads[grads.isnan()] = 0.0
+        scaling = torch.exp(v["scales"])
+        max_scale = torch.max(scaling, dim=1).values
+        # ---- densify_and_clone (:483-498)
+        sel_clone = torch.where(torch.norm(grads, dim=-1) >= max_grad, True, False)
+        sel_clone = torch.logical_and(sel_clone, max_scale <= percent_dense * extent)
+        idx_clone = torch.nonzero(sel_clone).flatten()
+        src1 = torch.cat((torch.arange(P, device=dev), idx_clone))           # source row of every row after the clone
+        fresh1 = torch.cat((torch.zeros(P, dtype=torch.bool, device=dev), torch.ones(idx_clone.numel(), dtype=torch.bool, device=dev)))
+        # ---- densify_and_split (:465-481): the statistics cover the first P rows only, clones see a padded gradient of 0
+        padded_grad = torch.zeros(src1.numel(), device=dev)
+        padded_grad[:grads.shape[0]] = grads.squeeze()
+        sel_split = torch.where(padded_grad >= max_grad, True, False)
+        sel_split = torch.logical_and(sel_split, max_scale[src1] > percent_dense * extent)
+        src_split = src1[sel_split]
+        stds = scaling[src_split].repeat(N, 1)
+        means = torch.zeros((stds.size(0), 3), device=dev)
+        samples = torch.normal(mean=means, std=stds)
+        rots = build_rotation(v["rotations"][src_split]).repeat(N, 1, 1)
+        child_xyz = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + v["means3D"][src_split].repeat(N, 1)
+        child_scale = torch.log(scaling[src_split].repeat(N, 1) / (0.8 * N))
+        n_child = child_xyz.size(0)
+        src2 = torch.cat((src1, src_split.repeat(N)))
+        fresh2 = torch.cat((fresh1, torch.ones(n_child, dtype=torch.bool, device=dev)))
+        child_of = torch.cat((torch.full((src1.numel(),), -1, dtype=torch.int64, device=dev), torch.arange(n_child, device=dev)))
+        keep = ~torch.cat((sel_split, torch.zeros(n_child, device=dev, dtype=torch.bool)))  # the split originals go
+        src3, fresh3, child3 = src2[keep], fresh2[keep], child_of[keep]
+        # ---- prune (:507-513)
+        is_child = child3 >= 0
+        scale3 = torch.where(is_child[:, None], child_scale[child3.clamp(min=0)], v["scales"][src3])
+        prune_mask = (torch.sigmoid(v["opacities"][src3]) < min_opacity).squeeze(-1)
+        if max_screen_size:
+            big_points_vs = torch.zeros_like(prune_mask)  # max_radii2D was reset to zeros by the densification above
+            big_points_ws = torch.exp(scale3).max(dim=1).values > 0.1 * extent
+            prune_mask = torch.logical_or(torch.logical_or(prune_mask, big_points_vs), big_points_ws)
+        keep2 = ~prune_mask
+        index, fresh, child = src3[keep2], fresh3[keep2], child3[keep2]
+        # ---- one row selection per buffer
+        new_params = select_rows(params, index)
+        ch = torch.nonzero(child >= 0).flatten()
+        new_params.views["means3D"][ch] = child_xyz[child[ch]]
+        new_params.views["scales"][ch] = child_scale[child[ch]]
+        new_grads = FlatGradients(index.numel(), dev, sh_coeffs=1 + params.shapes["features_rest"][1], num_class=params.shapes["segments"][1],
+                                  split_sh=True)
+        moment_index = torch.where(fresh, torch.full_like(index, -1), index)
+        holder = FlatGradients.__new__(FlatGradients)
+        holder.shapes, holder.split_sh = params.shapes, True
+        for name in ("exp_avg", "exp_avg_sq"):
+            holder.buffer = getattr(opt, name)
+            setattr(opt, name, select_rows(holder, moment_index).buffer)
+        opt.params, opt.grads = new_params, new_grads
+    return new_params, new_grads, index

@@ -124,7 +124,8 @@ def lib():
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.gsr_select_rows.restype = ctypes.c_int
     L.gsr_select_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
-                                  ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_void_p]
+                                  ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                                  ctypes.c_int32, ctypes.c_void_p]
     L.gsr_adam_step.restype = ctypes.c_int
     L.gsr_adam_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GsrAdamGroup), ctypes.c_int32,
                                 ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_void_p]

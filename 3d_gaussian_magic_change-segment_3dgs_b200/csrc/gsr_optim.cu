@@ -198,24 +198,22 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rows_kernel(const SelectAr
 } // namespace gsr
 
 extern "C" int gsr_select_rows(const float* src, float* dst, const int64_t* index, int64_t n_out, int64_t n_src, const int32_t* row_floats,
-                               int32_t num_blocks, gsr_stream_t stream_)
+                               const uint64_t* src_offsets, const uint64_t* dst_offsets, int32_t num_blocks, gsr_stream_t stream_)
 {
     if (n_out <= 0 || num_blocks <= 0) return 0;
-    if (!src || !dst || !index || !row_floats || num_blocks > SEL_MAX_BLOCKS || n_src < 0) {
+    if (!src || !dst || !index || !row_floats || !src_offsets || !dst_offsets || num_blocks > SEL_MAX_BLOCKS || n_src < 0) {
         set_error("gsr_select_rows: invalid argument (1 <= num_blocks <= %d)", SEL_MAX_BLOCKS);
         return GSR_ERR_INVALID_ARGUMENT;
     }
     SelectArgs a;
     a.src = src; a.dst = dst; a.index = (const long long*)index; a.n_out = n_out; a.n_src = n_src; a.num_blocks = num_blocks;
-    unsigned long long so = 0, dof = 0, chunks = 0;
+    unsigned long long chunks = 0;
     for (int k = 0; k < num_blocks; k++) {
         if (row_floats[k] <= 0) {
             set_error("gsr_select_rows: row_floats[%d] must be positive", k);
             return GSR_ERR_INVALID_ARGUMENT;
         }
-        a.row[k] = row_floats[k]; a.src_off[k] = so; a.dst_off[k] = dof; a.first_chunk[k] = (unsigned int)chunks;
-        so += (unsigned long long)row_floats[k] * (unsigned long long)n_src;
-        dof += (unsigned long long)row_floats[k] * (unsigned long long)n_out;
+        a.row[k] = row_floats[k]; a.src_off[k] = src_offsets[k]; a.dst_off[k] = dst_offsets[k]; a.first_chunk[k] = (unsigned int)chunks;
         chunks += ((unsigned long long)row_floats[k] * (unsigned long long)n_out + SEL_CHUNK - 1) / SEL_CHUNK;
     }
     a.first_chunk[num_blocks] = (unsigned int)chunks;

@@ -106,21 +106,32 @@ def multiview_step(leaves, cams, render_fn, loss_fn, rank=0, world=1, dist=None,
 # gradient rows straight into views of ONE flat fp32 buffer, which is then summed over ranks with a single NCCL all-reduce.
 # ---------------------------------------------------------------------------------------------------------------------
 class FlatGradients:
-    """[61 * P] fp32 buffer, tensor-major: means3D | shs | segments | opacities | scales | rotations. `views[name]` are
-    contiguous views shaped like the rasterizer inputs; they can be installed as the `.grad` of the leaves."""
+    """One flat fp32 buffer, tensor-major: means3D | shs | segments | opacities | scales | rotations (61 floats per Gaussian),
+    every block starting on a 256-byte boundary (the kernels load quaternions as float4 and segments as float2, so a block
+    must not start at an odd multiple of 4 bytes when P is odd). `views[name]` are contiguous views shaped like the rasterizer
+    inputs; they can be installed as the `.grad` of the leaves. `offsets()` gives (start, count) of every block."""
+    ALIGN = 64  # floats
 
     def __init__(self, P, device, sh_coeffs=16, num_class=2, split_sh=False):
         """split_sh=True: the raw-parameter layout (fused activations): features_dc | features_rest instead of shs."""
         sh = {"features_dc": (P, 1, 3), "features_rest": (P, sh_coeffs - 1, 3)} if split_sh else {"shs": (P, sh_coeffs, 3)}
         self.split_sh = split_sh
         self.shapes = {"means3D": (P, 3), **sh, "segments": (P, num_class), "opacities": (P, 1), "scales": (P, 3), "rotations": (P, 4)}
-        n = sum(int(torch.Size(s).numel()) for s in self.shapes.values())
-        self.buffer = torch.zeros(n, dtype=torch.float32, device=device)
-        self.views, off = {}, 0
+        self._offsets, off = {}, 0
         for name, shape in self.shapes.items():
             cnt = int(torch.Size(shape).numel())
-            self.views[name] = self.buffer[off:off + cnt].view(shape)
-            off += cnt
+            self._offsets[name] = (off, cnt)
+            off = (off + cnt + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.buffer = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views = {name: self.buffer[o:o + c].view(self.shapes[name]) for name, (o, c) in self._offsets.items()}
+
+    def offsets(self):
+        """dict block name -> (start, count) in floats."""
+        return dict(self._offsets)
+
+    def packed(self):
+        """The blocks without the alignment gaps, concatenated (a copy; for comparisons and checkpoints)."""
+        return torch.cat([v.reshape(-1) for v in self.views.values()])
 
     def backward_out(self, means2D_grad=None):
         """dict for `_backward_native(out=...)` (the native names differ from the leaf names for SH)."""

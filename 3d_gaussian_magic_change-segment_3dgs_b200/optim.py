@@ -21,7 +21,8 @@ GROUPS = {"xyz": "means3D", "f_dc": "features_dc", "f_rest": "features_rest", "o
 
 
 class FlatParameters(FlatGradients):
-    """[61 * P] fp32 buffer: means3D | features_dc | features_rest | segments | opacities | scales | rotations (raw values)."""
+    """Flat fp32 buffer: means3D | features_dc | features_rest | segments | opacities | scales | rotations (raw values, 61 floats
+    per Gaussian, blocks 256-byte aligned like FlatGradients)."""
 
     def __init__(self, P, device, sh_coeffs=16, num_class=2):
         super().__init__(P, device, sh_coeffs=sh_coeffs, num_class=num_class, split_sh=True)
@@ -35,14 +36,6 @@ class FlatParameters(FlatGradients):
             for name, view in fp.views.items():
                 view.copy_(tensors[name].reshape(view.shape))
         return fp
-
-    def offsets(self):
-        off, out = 0, {}
-        for name, shape in self.shapes.items():
-            n = int(torch.Size(shape).numel())
-            out[name] = (off, n)
-            off += n
-        return out
 
 
 class FusedAdam:
@@ -68,11 +61,16 @@ class FusedAdam:
         """update_learning_rate (scene/gaussian_model.py:184-190) sets the xyz group's rate every iteration."""
         self.lrs[GROUPS.get(group, group)] = float(lr)
 
-    def step(self):
+    def step(self, skip=()):
+        """One Adam step. `skip`: parameter groups left untouched this step (torch.optim.Adam skips a parameter whose .grad is
+        None, which is what happens to a tensor the reference has just replaced -- reset_opacity, densification)."""
         L = _lib.lib()
-        self.step_count += 1
+        skip = {GROUPS.get(k, k) for k in skip}
         offs = self.params.offsets()
-        names = [n for n in offs if n in self.lrs]
+        names = [n for n in offs if n in self.lrs and n not in skip]
+        if not names:
+            return
+        self.step_count += 1
         arr = (_lib.GsrAdamGroup * len(names))(*[_lib.GsrAdamGroup(offs[n][0], offs[n][1], self.lrs[n]) for n in names])
         dev = self.params.buffer.device
         with torch.cuda.device(dev):
@@ -101,9 +99,12 @@ def select_rows(flat, index):
     else:
         out = FlatGradients(n_out, dev, sh_coeffs=sh_coeffs, num_class=num_class, split_sh=flat.split_sh)
     rows = [int(torch.Size(s[1:]).numel()) for s in flat.shapes.values()]
-    arr = (ctypes.c_int32 * len(rows))(*rows)
+    nb = len(rows)
+    arr = (ctypes.c_int32 * nb)(*rows)
+    so = (ctypes.c_uint64 * nb)(*[flat.offsets()[k][0] for k in flat.shapes])
+    do = (ctypes.c_uint64 * nb)(*[out.offsets()[k][0] for k in flat.shapes])
     with torch.cuda.device(dev):
-        rc = L.gsr_select_rows(flat.buffer.data_ptr(), out.buffer.data_ptr(), idx.data_ptr(), n_out, n_src, arr, len(rows),
+        rc = L.gsr_select_rows(flat.buffer.data_ptr(), out.buffer.data_ptr(), idx.data_ptr(), n_out, n_src, arr, so, do, nb,
                                torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "gsr_select_rows")
     return out
@@ -188,7 +189,7 @@ def densify_and_prune(params, opt, xyz_gradient_accum, denom, max_grad, min_opac
                                   split_sh=True)
         moment_index = torch.where(fresh, torch.full_like(index, -1), index)
         holder = FlatGradients.__new__(FlatGradients)
-        holder.shapes, holder.split_sh = params.shapes, True
+        holder.shapes, holder.split_sh, holder._offsets = params.shapes, True, params.offsets()
         for name in ("exp_avg", "exp_avg_sq"):
             holder.buffer = getattr(opt, name)
             setattr(opt, name, select_rows(holder, moment_index).buffer)

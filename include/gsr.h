@@ -216,10 +216,11 @@ int gsr_image_loss(const float* image, const float* gt, int32_t C, int32_t H, in
 
 /* Densify / prune as one index list (replaces the per-tensor boolean masks and torch.cat of
  * scene/gaussian_model.py:377-441 over seven parameters and their two Adam moments). src and dst are flat buffers of
- * num_blocks blocks; block k holds n_src (resp. n_out) rows of row_floats[k] floats. Row j of every dst block = row index[j]
- * of the matching src block; index[j] == -1 gives a row of zeros (the moments of a freshly cloned / split Gaussian). One launch. */
+ * num_blocks blocks; block k starts at float src_offsets[k] (resp. dst_offsets[k]) and holds n_src (resp. n_out) rows of
+ * row_floats[k] floats. Row j of every dst block = row index[j] of the matching src block; index[j] == -1 gives a row of
+ * zeros (the moments of a freshly cloned / split Gaussian). One launch. */
 int gsr_select_rows(const float* src, float* dst, const int64_t* index, int64_t n_out, int64_t n_src, const int32_t* row_floats,
-                    int32_t num_blocks, gsr_stream_t stream);
+                    const uint64_t* src_offsets, const uint64_t* dst_offsets, int32_t num_blocks, gsr_stream_t stream);
 
 /* Number of visible Gaussians of the most recent gsr_forward on the calling thread. */
 uint32_t gsr_last_num_visible(void);

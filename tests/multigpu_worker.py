@@ -40,12 +40,12 @@ sets = [mv.native_view_backward_packets(D, gs, rs, fwd, ug)]
 campos = [[c["campos"].to(dev)] for c in cams]
 mv.exchange_packets(D, dist, flat, gs, sets, campos, 3, world)
 torch.cuda.synchronize()
-err = float((flat.buffer - dense.buffer).abs().max()) / float(dense.buffer.abs().max())
+err = float((flat.packed() - dense.packed()).abs().max()) / float(dense.packed().abs().max())
 assert err <= 2e-5, err  # two backward runs: fp32 atomic-order noise
 # replicas bitwise identical
-ref = flat.buffer.clone()
+ref = flat.packed()
 dist.broadcast(ref, 0)
-assert torch.equal(ref, flat.buffer), "replicas differ"
+assert torch.equal(ref, flat.packed()), "replicas differ"
 # peer-memory path: blobs written into peer-visible buffers, gather kernel pulls them over NVLink (3 steps: both buffers)
 px = mv.PeerPacketExchange(D, dist, P, 1, rank, world, dev)
 for step in range(3):
@@ -55,11 +55,11 @@ for step in range(3):
     px.exchange(peer, gs, campos, 3)
     torch.cuda.synchronize()
     assert int(cnt) == sets[0][2]
-    err_p = float((peer.buffer - dense.buffer).abs().max()) / float(dense.buffer.abs().max())
+    err_p = float((peer.packed() - dense.packed()).abs().max()) / float(dense.packed().abs().max())
     assert err_p <= 2e-5, (step, err_p)
-    ref = peer.buffer.clone()
+    ref = peer.packed()
     dist.broadcast(ref, 0)
-    assert torch.equal(ref, peer.buffer), "peer replicas differ"
+    assert torch.equal(ref, peer.packed()), "peer replicas differ"
 px.close()
 # raw-parameter layout end to end: flat parameters -> fused-activation forward -> packets into peer buffers -> gather into the
 # split flat gradient buffer -> fused Adam; replicas must stay bitwise identical after the optimiser step
@@ -80,7 +80,7 @@ dense_r.allreduce(dist)
 px2.view_backward(params.views, rs, fwd_r, ug, 0)
 px2.exchange(rgrads, params.views, campos, 3)
 torch.cuda.synchronize()
-err_r = float((rgrads.buffer - dense_r.buffer).abs().max()) / float(dense_r.buffer.abs().max())
+err_r = float((rgrads.packed() - dense_r.packed()).abs().max()) / float(dense_r.packed().abs().max())
 assert err_r <= 2e-5, err_r
 before = params.buffer.clone()
 opt.step()

@@ -167,7 +167,7 @@ def test_accumulate_mode_sums_views_into_flat_buffer():
     for leaf, nat in names.items():
         exp = dense[0][nat] + dense[1][nat]
         assert H.rel_linf(flat.views[leaf], exp) <= 2e-5, leaf
-    assert flat.buffer.numel() == 61 * P
+    assert sum(c for _, c in flat.offsets().values()) == 61 * P and flat.buffer.numel() >= 61 * P
 
 
 def test_gradient_packets_rebuild_dense_rows():
@@ -230,7 +230,7 @@ def test_gradient_packets_rebuild_dense_rows():
     rmw = mv.FlatGradients(P, "cuda")
     for (blob, cnt, n), cp in zip(sets, campos):
         D.apply_packets(gs["means3D"], cp, 3, 16, D.packet_blob_views(blob, P)[0], cnt, rmw.backward_out())
-    assert H.rel_linf(rmw.buffer, flat.buffer) <= 1e-6
+    assert H.rel_linf(rmw.packed(), flat.packed()) <= 1e-6
     # sticky capacity: the second step's blobs are produced at the exchange's capacity and gathered without repacking
     st = {}
     mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1, state=st)

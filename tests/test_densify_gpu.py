@@ -147,7 +147,7 @@ def test_densify_and_prune_matches_reference_algorithm(P, max_screen_size):
                                                            percent_dense=pd)
     Pn = ref.p["xyz"].shape[0]
     assert new_params.views["means3D"].shape[0] == Pn == index.numel() and Pn != P
-    assert new_grads.buffer.numel() == new_params.buffer.numel() == 61 * Pn
+    assert new_grads.buffer.numel() == new_params.buffer.numel() >= 61 * Pn
     noffs = new_params.offsets()
     for n, k in NAMES.items():
         assert torch.equal(new_params.views[k], ref.p[n].detach().reshape(new_params.views[k].shape)), n
@@ -168,7 +168,7 @@ def test_select_rows_basics():
     mv = importlib.import_module(H.PKG_NAME + ".multiview")
     P = 1000
     f = mv.FlatGradients(P, "cuda")
-    f.buffer.copy_(torch.arange(61 * P, dtype=torch.float32))
+    f.buffer.copy_(torch.arange(f.buffer.numel(), dtype=torch.float32))
     idx = torch.tensor([5, -1, 999, 0, 5], device="cuda")
     out = optim.select_rows(f, idx)
     for name, view in out.views.items():

@@ -89,6 +89,6 @@ def test_cfg3_backward_linearity_and_packet_exchange(cfg3):
     sets = [mv.native_view_backward_packets(D, gs, rs, fwd, ug2)]
     assert sets[0][2] == int((fwd[5] > 0).sum())
     mv.exchange_packets(D, None, flat, gs, sets, [[cam["campos"].cuda()]], 3, world=1)
-    assert H.rel_linf(flat.buffer, two.buffer) <= 2e-5
+    assert H.rel_linf(flat.packed(), two.packed()) <= 2e-5
     vis = fwd[5] > 0
     assert float(flat.views["shs"][~vis].abs().max()) == 0.0 and float(flat.views["means3D"][~vis].abs().max()) == 0.0

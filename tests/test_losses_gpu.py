@@ -51,7 +51,7 @@ def test_l1_ssim_loss_and_gradient_match_torch(C, Hh, W, lam):
     got.backward()
     stats, _ = losses.l1_ssim_loss_and_grad(img, gt, lam, want_grad=False)
     assert abs(float(got.detach()) - float(want.detach())) <= 1e-5, (float(got.detach()), float(want.detach()))
-    assert abs(float(stats[0]) - float(l1)) <= 1e-5 and abs(float(stats[1]) - float(ssim)) <= 1e-5
+    assert abs(float(stats[0]) - float(l1.detach())) <= 1e-5 and abs(float(stats[1]) - float(ssim.detach())) <= 1e-5
     assert H.rel_linf(b.grad, a.grad) <= 1e-4, H.rel_linf(b.grad, a.grad)
     # deterministic: no float atomics anywhere
     got2 = losses.l1_ssim_loss(img.clone().requires_grad_(True), gt, lam)

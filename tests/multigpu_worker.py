@@ -90,6 +90,29 @@ ref = params.buffer.clone()
 dist.broadcast(ref, 0)
 assert torch.equal(ref, params.buffer), "parameter replicas differ after the fused Adam step"
 px2.close()
+# the native training driver on all ranks: 2 x world views per step, densification at step 3, opacity reset at step 4; replicas
+# must hold bitwise-identical parameters and Adam moments after every step
+trainer = importlib.import_module(H.PKG_NAME + ".trainer")
+o = trainer.OptimizationParams(densify_from_iter=1, densification_interval=3, opacity_reset_interval=4, densify_until_iter=100)
+init = {k: v.clone() for k, v in params.views.items()}
+tr = trainer.NativeTrainer(D, init, o, cameras_extent=5.0, bg=bg, dist=dist, rank=rank, world=world)
+tr.active_sh_degree = 3
+B = 2 * world
+tcams = [dict(syn.make_camera(W, Hh, yaw_deg=20.0 * i), image_width=W, image_height=Hh) for i in range(B)]
+gg = torch.Generator().manual_seed(3)
+tgts = [torch.rand(3, Hh, W, generator=gg).to(dev) for _ in range(B)]
+sizes = []
+for it in range(5):
+    loss = tr.train_step(tcams, tgts)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(loss))
+    sizes.append(tr.P)
+    for buf in (tr.params.packed(), tr.opt.exp_avg, tr.opt.exp_avg_sq):
+        ref = buf.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, buf), "trainer replicas differ at step %d" % (it + 1)
+assert len(set(sizes)) > 1, sizes  # the model was rebuilt by the densification
+tr.close()
 # a rank that cannot set up peer buffers makes EVERY rank raise PeerUnavailable (no hang, no half-open state)
 if rank == world - 1:
     os.environ["GSR_PEER_DISABLE"] = "1"

@@ -213,3 +213,57 @@ def test_graft_entry_build_runs():
     entry = importlib.import_module("__graft_entry__")
     entry.build()
     assert callable(entry.smoke)
+
+
+def test_ply_checkpoint_layout_and_round_trip(tmp_path):
+    """io_ply against the reference's file layout (scene/gaussian_model.py:186-233, :262-309): the header plyfile writes for it,
+    channel-major SH blocks, and an independently packed file."""
+    import importlib
+    import struct
+
+    import numpy as np
+    import torch
+
+    import helpers as H
+
+    H.pkg()
+    io = importlib.import_module(H.PKG_NAME + ".io_ply")
+    optim = importlib.import_module(H.PKG_NAME + ".optim")
+    g = torch.Generator().manual_seed(0)
+    P = 7
+    t = {"means3D": torch.randn(P, 3, generator=g), "features_dc": torch.randn(P, 1, 3, generator=g), "features_rest": torch.randn(P, 15, 3, generator=g),
+         "opacities": torch.randn(P, 1, generator=g), "segments": torch.randn(P, 2, generator=g), "scales": torch.randn(P, 3, generator=g),
+         "rotations": torch.randn(P, 4, generator=g)}
+    path = str(tmp_path / "point_cloud" / "iteration_7" / "point_cloud.ply")
+    io.save_ply(path, t)
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    lines = head.decode().splitlines()
+    names = io.attribute_names(16, 2)
+    assert lines[:3] == ["ply", "format binary_little_endian 1.0", "element vertex 7"]
+    assert lines[3:] == ["property float %s" % n for n in names] and len(names) == 6 + 3 + 45 + 1 + 2 + 3 + 4
+    assert len(body) == P * len(names) * 4
+    row0 = np.frombuffer(body[:len(names) * 4], "<f4")
+    assert np.array_equal(row0[:3], t["means3D"][0].numpy()) and np.all(row0[3:6] == 0)  # normals are zeros
+    assert np.array_equal(row0[6:9], t["features_dc"][0, 0].numpy())
+    # f_rest is channel-major: f_rest_k = features_rest[:, k % 15, k // 15]
+    assert row0[9 + 17] == float(t["features_rest"][0, 2, 1]) and row0[9 + 44] == float(t["features_rest"][0, 14, 2])
+    back = io.load_ply(path)
+    for k in t:
+        assert torch.equal(back[k], t[k]), k
+    fp = optim.FlatParameters.from_tensors(back)  # loads straight into the flat parameter buffer
+    assert torch.equal(fp.views["rotations"], t["rotations"])
+    # an independently packed file (what plyfile would write for the reference), different property order of the tail
+    hdr = "ply\nformat binary_little_endian 1.0\ncomment made by hand\nelement vertex 2\n" + "".join("property float %s\n" % n for n in names) + "end_header\n"
+    rows = [[float(100 * r + i) for i in range(len(names))] for r in range(2)]
+    p2 = str(tmp_path / "hand.ply")
+    with open(p2, "wb") as f:
+        f.write(hdr.encode())
+        for r in rows:
+            f.write(struct.pack("<%df" % len(names), *r))
+    h = io.load_ply(p2)
+    assert h["means3D"].tolist() == [[0.0, 1.0, 2.0], [100.0, 101.0, 102.0]]
+    assert h["features_dc"].shape == (2, 1, 3) and h["features_dc"][1, 0].tolist() == [106.0, 107.0, 108.0]
+    assert h["features_rest"].shape == (2, 15, 3) and float(h["features_rest"][0, 2, 1]) == 9.0 + 17.0
+    assert float(h["opacities"][1, 0]) == 154.0 and h["segments"][0].tolist() == [55.0, 56.0]
+    assert h["scales"][0].tolist() == [57.0, 58.0, 59.0] and h["rotations"][0].tolist() == [60.0, 61.0, 62.0, 63.0]

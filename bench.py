@@ -679,7 +679,6 @@ def run_cpu_baseline(syn, workload, row_stride=1):
     # re-run the sampled compositing alone to measure it.
     L = O.lib()
     tc0 = time.time()
-    fwd_only = O.forward  # noqa: F841  (kept for clarity)
     nc = np.zeros(W * Hh, np.uint32)
     col, seg, dep, alp = np.zeros((3, Hh, W), np.float32), np.zeros((2, Hh, W), np.float32), np.zeros((1, Hh, W), np.float32), np.zeros((1, Hh, W), np.float32)
     L.orc_render_forward(O._i(W), O._i(Hh), O._i(2), O._p(st["ranges"]), O._p(st["point_list"]), O._p(st["means2D"]), O._p(st["rgb"]),

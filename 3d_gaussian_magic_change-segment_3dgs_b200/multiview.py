@@ -147,29 +147,6 @@ class FlatGradients:
     def allreduce(self, dist, group=None):
         dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
 
-    def zero_async(self):
-        """Zero the buffer on a side stream (call at the START of a step, when last step's gradients have been consumed): the
-        1.46 GB fill then overlaps the step's forward/backward instead of sitting in front of the packet rebuild."""
-        if not self.buffer.is_cuda:
-            self.buffer.zero_()
-            return
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.buffer.device)
-        self._side.wait_stream(torch.cuda.current_stream(self.buffer.device))
-        with torch.cuda.stream(self._side):
-            self.buffer.zero_()
-            self._zeroed = torch.cuda.Event()
-            self._zeroed.record(self._side)
-
-    def wait_zeroed(self):
-        """Make the current stream wait for zero_async(); falls back to a synchronous fill if it was not called."""
-        ev = getattr(self, "_zeroed", None)
-        if ev is None:
-            self.buffer.zero_()
-        else:
-            torch.cuda.current_stream(self.buffer.device).wait_event(ev)
-            self._zeroed = None
-
 
 def native_view_backward(D, leaves, rs, fwd, upstream, flat, first, means2D_grad=None):
     """Backward of one view into the flat buffer: overwrite (zero-fill + visible rows) for the step's first local view,

@@ -1,4 +1,5 @@
-"""One small program that launches every kernel of the library at cfg3 a few times, for `ncu --set full` (profiles/README.md):
+"""One small program that launches every kernel of the library a few times (default cfg3), for `ncu --set full` (profiles/README.md)
+and, at cfg1, for `compute-sanitizer --tool memcheck`:  python scripts/profile_step.py [iterations] [workload]
 classic forward + dense backward, the raw-parameter entry, packets backward + gather over 2 views, L1+SSIM loss, fused Adam."""
 import importlib
 import os
@@ -12,14 +13,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers as H  # noqa: E402
 
 ITERS = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+WORKLOAD = sys.argv[2] if len(sys.argv) > 2 else "cfg3"  # cfg1 (100k Gaussians, 800x800) is small enough for compute-sanitizer
 Pk = H.pkg()
 mv = importlib.import_module(H.PKG_NAME + ".multiview")
 optim = importlib.import_module(H.PKG_NAME + ".optim")
 losses = importlib.import_module(H.PKG_NAME + ".losses")
 D = Pk.diff_gaussian_rasterization
 syn = H.synthetic()
-P, W, Hh, seed = syn.CONFIGS["cfg3"]
-gs, cam = syn.make_scene("cfg3")
+P, W, Hh, seed = syn.CONFIGS[WORKLOAD]
+gs, cam = syn.make_scene(WORKLOAD)
 gs = H.to_dev(gs)
 ug = H.to_dev(syn.upstream_grads(W, Hh, seed, with_depth=True))
 rs = H.settings(cam, torch.zeros(3))

@@ -26,6 +26,7 @@ class GsrGaussians(ctypes.Structure):
         ("means3D", ctypes.c_void_p), ("shs", ctypes.c_void_p), ("colors_precomp", ctypes.c_void_p), ("segments", ctypes.c_void_p),
         ("opacities", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p), ("cov3D_precomp", ctypes.c_void_p),
         ("shs_rest", ctypes.c_void_p), ("raw_params", ctypes.c_int32),
+        ("subset", ctypes.c_void_p), ("subset_count", ctypes.c_int32),
     ]
 
 

@@ -167,6 +167,10 @@ static int validate(const GsrView* view, const GsrGaussians* in)
             return GSR_ERR_INVALID_ARGUMENT;
         }
     }
+    if (in->subset && in->subset_count < 0) {
+        set_error("subset_count must be >= 0");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
     if (in->raw_params) {
         if (in->cov3D_precomp || !sr) {
             set_error("raw_params needs scales + rotations (log-scales, un-normalised quaternions), not cov3D_precomp");
@@ -212,13 +216,14 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
     int rc = validate(view, in);
     if (rc) return rc;
     if (num_rendered) *num_rendered = 0;
-    if (in->P == 0) return 0;
+    if (in->P == 0 || (in->subset && in->subset_count == 0)) return 0;
     if (!out || !out->color || !out->depth || !out->alpha || !out->radii || (view->num_class == 2 && !out->segment) || !alloc) {
         set_error("missing output pointers or allocator");
         return GSR_ERR_INVALID_ARGUMENT;
     }
     const bool debug = view->debug != 0;
-    const int P = in->P, W = view->image_width, H = view->image_height;
+    const int P = in->subset ? in->subset_count : in->P; // Gaussians rendered (= positions of the per-Gaussian state and of radii)
+    const int W = view->image_width, H = view->image_height;
     const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
     const uint32_t T = (uint32_t)gx * (uint32_t)gy;
     const size_t N = (size_t)W * H;
@@ -250,7 +255,7 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
     pa.P = P; pa.D = view->sh_degree; pa.M = in->shs ? view->sh_coeffs : 0; pa.S = in->segments ? view->num_class : 0;
     pa.means3D = in->means3D; pa.scales = in->scales; pa.scale_modifier = view->scale_modifier; pa.rotations = in->rotations;
     pa.opacities = in->opacities; pa.shs = in->shs; pa.cov3D_precomp = in->cov3D_precomp; pa.colors_precomp = in->colors_precomp;
-    pa.shs_rest = in->shs_rest; pa.raw = in->raw_params;
+    pa.shs_rest = in->shs_rest; pa.raw = in->raw_params; pa.subset = in->subset;
     pa.segments = in->segments; pa.view = view->viewmatrix; pa.proj = view->projmatrix; pa.campos = view->campos;
     pa.W = W; pa.H = H; pa.tan_fovx = view->tanfovx; pa.tan_fovy = view->tanfovy;
     pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:226-227
@@ -493,7 +498,12 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
 {
     int rc = validate(view, in);
     if (rc) return rc;
-    if (in->P == 0) return 0;
+    if (in->P == 0 || (in->subset && in->subset_count == 0)) return 0;
+    if (in->subset && packets) {
+        set_error("gsr_backward_packets does not take an index list (subset)");
+        return GSR_ERR_UNSUPPORTED;
+    }
+    const int count = in->subset ? in->subset_count : in->P; // rendered Gaussians: sizes of the saved state
     if (!radii || !state || !state->geom || !state->img || !alpha || !pix || !pix->dL_dcolor || !grads || !scratch) {
         set_error("gsr_backward: missing argument");
         return GSR_ERR_INVALID_ARGUMENT;
@@ -502,8 +512,8 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
         set_error("gsr_backward: binning state missing");
         return GSR_ERR_INVALID_ARGUMENT;
     }
-    if (scratch_bytes < gsr_backward_scratch_bytes(in->P)) {
-        set_error("gsr_backward: scratch too small (%zu < %zu)", scratch_bytes, gsr_backward_scratch_bytes(in->P));
+    if (scratch_bytes < gsr_backward_scratch_bytes(count)) {
+        set_error("gsr_backward: scratch too small (%zu < %zu)", scratch_bytes, gsr_backward_scratch_bytes(count));
         return GSR_ERR_INVALID_ARGUMENT;
     }
     const bool debug = view->debug != 0;
@@ -512,7 +522,7 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     const uint32_t T = (uint32_t)gx * (uint32_t)gy;
 
     GeomState g;
-    geom_layout((char*)state->geom, P, g);
+    geom_layout((char*)state->geom, count, g);
     ImgState img;
     img_layout((char*)state->img, (size_t)W * H, T, img);
     float* grad_rec = (float*)align_up((size_t)scratch, 256);
@@ -528,6 +538,7 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     pb.radii = radii; pb.g = g; pb.grad_rec = grad_rec; pb.out = *grads;
     pb.colors_precomp_given = in->colors_precomp != nullptr;
     pb.packets = packets; pb.packet_capacity = capacity; pb.packet_count = count_dev; pb.vis_index = vis_index;
+    pb.has_subset = in->subset != nullptr;
     if (!in->shs) { pb.out.dL_dsh = nullptr; pb.out.dL_dsh_rest = nullptr; }
     if (!in->raw_params) pb.out.dL_dsh_rest = nullptr;
     if (in->raw_params && pb.out.dL_dsh && view->sh_coeffs > 1 && !pb.out.dL_dsh_rest && !packets) {

@@ -155,6 +155,7 @@ struct PreFwdArgs
     const float* segments;
     const float* shs_rest; // raw-parameter mode: shs = [P,1,3], shs_rest = [P,M-1,3]
     int raw;               // activations inside the kernel (GsrGaussians.raw_params)
+    const int32_t* subset; // index-list rendering: position idx < P reads input row subset[idx] (P = the list length)
     const float* view;
     const float* proj;
     const float* campos;
@@ -195,6 +196,7 @@ struct PreBwdArgs
     uint32_t* packet_count;
     uint32_t* vis_index;
     int fill; // set by launch_preprocess_bwd: dense mode, the kernel zero-fills the rows its CTA owns
+    int has_subset; // index-list rendering: a CTA's slots are not the gradient rows [256 b, 256 b + 256)
 };
 
 struct GatherPacketsArgs

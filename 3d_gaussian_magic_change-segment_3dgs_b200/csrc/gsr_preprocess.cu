@@ -52,8 +52,10 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
     unsigned clamp_bits = 0;
     uint32_t tiles = 0;
 
+    int gid = idx; // row of the input tensors: the position itself, or the list entry when an index list is rendered
     if (idx < a.P) {
-        const float3 p_orig = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+        if (a.subset) gid = a.subset[idx];
+        const float3 p_orig = {a.means3D[3 * gid], a.means3D[3 * gid + 1], a.means3D[3 * gid + 2]};
         // near cull (auxiliary.h:139-164); the +-1.3 NDC test is disabled in the reference
         const float4 p_hom = xform_point_h(p_orig, s_proj);
         const float p_w = 1.0f / (p_hom.w + 0.0000001f);
@@ -65,10 +67,10 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
             float cov3D[6];
             if (a.cov3D_precomp != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) cov3D[i] = a.cov3D_precomp[6 * (size_t)idx + i];
+                for (int i = 0; i < 6; i++) cov3D[i] = a.cov3D_precomp[6 * (size_t)gid + i];
             } else {
-                float3 sc = {a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]};
-                float4 q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+                float3 sc = {a.scales[3 * gid], a.scales[3 * gid + 1], a.scales[3 * gid + 2]};
+                float4 q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)gid);
                 if (a.raw) { // fused activations (scene/gaussian_model.py:100-106): exp, normalize
                     sc = {expf(sc.x), expf(sc.y), expf(sc.z)};
                     q = act_normalize(q);
@@ -93,19 +95,19 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
                     if (a.colors_precomp == nullptr) {
                         const float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
                         const float3* sh3 = reinterpret_cast<const float3*>(a.shs);
-                        const ShCoeffs<float3> sh = a.raw ? ShCoeffs<float3>{sh3 + idx, reinterpret_cast<const float3*>(a.shs_rest) + (size_t)idx * (a.M - 1)}
-                                                          : ShCoeffs<float3>{sh3 + (size_t)idx * a.M, sh3 + (size_t)idx * a.M + 1};
+                        const ShCoeffs<float3> sh = a.raw ? ShCoeffs<float3>{sh3 + gid, reinterpret_cast<const float3*>(a.shs_rest) + (size_t)gid * (a.M - 1)}
+                                                          : ShCoeffs<float3>{sh3 + (size_t)gid * a.M, sh3 + (size_t)gid * a.M + 1};
                         rgb = sh_to_rgb(a.D, p_orig, campos, sh, clamp_bits);
                     } else {
-                        rgb = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
+                        rgb = {a.colors_precomp[3 * gid], a.colors_precomp[3 * gid + 1], a.colors_precomp[3 * gid + 2]};
                     }
                     float s0 = 0.f, s1 = 0.f;
                     if (a.S == 2 && a.segments != nullptr) {
-                        const float2 sg = *reinterpret_cast<const float2*>(a.segments + 2 * (size_t)idx);
+                        const float2 sg = *reinterpret_cast<const float2*>(a.segments + 2 * (size_t)gid);
                         s0 = a.raw ? act_sigmoid(sg.x) : sg.x;
                         s1 = a.raw ? act_sigmoid(sg.y) : sg.y;
                     }
-                    const float op = a.raw ? act_sigmoid(a.opacities[idx]) : a.opacities[idx];
+                    const float op = a.raw ? act_sigmoid(a.opacities[gid]) : a.opacities[gid];
                     radius_out = my_radius;
                     A = {point_image.x, point_image.y, conic.x, conic.y};
                     B = {conic.z, op, rgb.x, rgb.y};
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
         a.g.rec[3 * (size_t)slot + 1] = B;
         a.g.rec[3 * (size_t)slot + 2] = C;
         a.g.rect[slot] = rect;
-        a.g.slot_gid[slot] = (uint32_t)idx;
+        a.g.slot_gid[slot] = (uint32_t)gid; // the backward addresses inputs and gradient rows through this
         a.g.clamped[slot] = (uint8_t)clamp_bits;
     }
     // instance count of the block -> global R (integer atomics: deterministic total)
@@ -818,7 +820,7 @@ int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
             const size_t W = (P + 31) / 32;
             GSR_CUDA(cudaMemsetAsync(a.vis_index, 0, 2 * W * sizeof(uint32_t), s));
         }
-    } else if (!a.out.accumulate && !fill_in_kernel()) {
+    } else if (!a.out.accumulate && (!fill_in_kernel() || a.has_subset)) {
         for (auto& f : fills)
             if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
     }
@@ -829,7 +831,7 @@ int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
     PreBwdArgs b = a;
-    b.fill = (!a.packets && !a.out.accumulate && fill_in_kernel()) ? 1 : 0;
+    b.fill = (!a.packets && !a.out.accumulate && fill_in_kernel() && !a.has_subset) ? 1 : 0;
     preprocess_bwd_kernel<<<a.g.nblk, BWD_THREADS, 0, s>>>(b); count_launches(1);
     return 0;
 }

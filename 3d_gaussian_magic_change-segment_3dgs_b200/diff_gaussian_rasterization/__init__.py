@@ -102,17 +102,31 @@ def _view_struct(rs, M, num_class, keep):
                    _ptr(bg), _ptr(vm), _ptr(pm), _ptr(cp))
 
 
-def rasterize_gaussians(means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+                        subset=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp,
-                                     raster_settings)
+                                     raster_settings, subset)
 
 
-def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, rs, sh_rest=None, raw_params=False):
+def _subset(subset, device):
+    """int32 contiguous index list on the compute device, or None."""
+    if subset is None:
+        return None
+    if subset.device != device:
+        raise RuntimeError("subset must be on %s; libgsr has no CPU path" % (device,))
+    return subset.to(torch.int32).contiguous()
+
+
+def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, rs, sh_rest=None, raw_params=False,
+                    subset=None):
     """RasterizeGaussiansCUDA (rasterize_points.cu:35-125) over gsr_forward. Returns the reference's 9-tuple
     (num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer).
 
     raw_params=True (fused activations, GsrGaussians.raw_params): the tensors are the model's RAW parameters -- opacity /
-    segment logits, log-scales, un-normalised quaternions, sh = _features_dc [P,1,3] and sh_rest = _features_rest [P,M-1,3]."""
+    segment logits, log-scales, un-normalised quaternions, sh = _features_dc [P,1,3] and sh_rest = _features_rest [P,M-1,3].
+
+    subset (int32 CUDA tensor, strictly ascending row numbers): render only those Gaussians without materialising masked copies
+    (GsrGaussians.subset); radii then has one entry per list element."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -140,13 +154,18 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
         t_seg, t_op = _prep(segments, device, "segments"), _prep(opacities, device, "opacities")
         t_sc, t_rot = _prep(scales, device, "scales"), _prep(rotations, device, "rotations")
         t_cov = _prep(cov3Ds_precomp, device, "cov3Ds_precomp")
+        t_sub = _subset(subset, device)
+        count = P if t_sub is None else int(t_sub.numel())
         gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), _ptr(t_op), _ptr(t_sc), _ptr(t_rot), _ptr(t_cov),
-                           _ptr(t_rest), int(bool(raw_params)))
+                           _ptr(t_rest), int(bool(raw_params)), _ptr(t_sub), count if t_sub is not None else 0)
         color = torch.empty((NUM_CHANNELS, H, W), **opts)
         segment = torch.empty((num_class, H, W), **opts)
         depth = torch.empty((1, H, W), **opts)
         alpha = torch.empty((1, H, W), **opts)
-        radii = torch.empty(P, dtype=torch.int32, device=device)
+        radii = torch.empty(count, dtype=torch.int32, device=device)
+        if count == 0:  # an empty index list: like P == 0, the core is skipped and the images stay zero
+            eb = lambda: torch.empty(0, dtype=torch.uint8, device=device)
+            return 0, color.zero_(), depth.zero_(), segment.zero_(), alpha.zero_(), radii, eb(), eb(), eb()
         out = GsrOutputs(color.data_ptr(), segment.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii.data_ptr())
         alloc = _Alloc(device)
         R = ctypes.c_int32(0)
@@ -163,7 +182,7 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
 
 def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotations, cov3Ds_precomp, grad_color, grad_segment, grad_depth,
                      grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, needs=None, out=None, accumulate=False,
-                     sh_rest=None, raw_params=False, opacities=None):
+                     sh_rest=None, raw_params=False, opacities=None, subset=None):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:127-221) over gsr_backward. Returns a dict of dense
     gradients (zeros for invisible Gaussians). `needs` optionally names the gradients to produce.
 
@@ -219,8 +238,16 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
         if raw_params and t_op is None:
             raise RuntimeError("raw_params backward needs the raw opacities")
         t_rest = _prep(sh_rest, device, "sh_rest") if raw_params else None
+        t_sub = _subset(subset, device)
+        count = P if t_sub is None else int(t_sub.numel())
         gin = GsrGaussians(P, _ptr(t_means), _ptr(t_sh), _ptr(t_col), _ptr(t_seg), t_op.data_ptr() if raw_params else t_means.data_ptr(),
-                           _ptr(t_sc), _ptr(t_rot), _ptr(t_cov), _ptr(t_rest), int(bool(raw_params)))
+                           _ptr(t_sc), _ptr(t_rot), _ptr(t_cov), _ptr(t_rest), int(bool(raw_params)), _ptr(t_sub),
+                           count if t_sub is not None else 0)
+        if count == 0:  # nothing was rendered: every gradient row is zero
+            for t in grads.values():
+                if t is not None and not accumulate:
+                    t.zero_()
+            return grads
         g_col = _prep(grad_color, device, "grad_color")
         if g_col is None:
             g_col = torch.zeros((NUM_CHANNELS, H, W), **opts)
@@ -230,7 +257,7 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
                            _ptr(grads["segments"]), _ptr(grads["opacities"]), _ptr(grads["scales"]), _ptr(grads["rotations"]),
                            _ptr(grads["cov3Ds_precomp"]), int(bool(accumulate)), _ptr(grads["sh_rest"]))
         state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
-        nscratch = L.gsr_backward_scratch_bytes(P)
+        nscratch = L.gsr_backward_scratch_bytes(count)
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
         t_radii = radii.contiguous()
         t_alpha = _prep(alpha, device, "alpha")
@@ -406,19 +433,21 @@ def apply_packets(means3D, campos, sh_degree, sh_coeffs, packets, count, out, nu
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    def forward(ctx, means3D, means2D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+                subset=None):
         args = (means3D, sh, colors_precomp, segments, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
         if raster_settings.debug:
             cpu_args = cpu_deep_copy_tuple(args[:-1] + tuple(raster_settings))  # copy before they can be corrupted
             try:
-                num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer = _forward_native(*args)
+                num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer = _forward_native(*args, subset=subset)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer = _forward_native(*args)
+            num_rendered, color, depth, segment, alpha, radii, geomBuffer, binningBuffer, imgBuffer = _forward_native(*args, subset=subset)
 
+        ctx.subset = subset
         ctx.raster_settings = raster_settings
         ctx.num_rendered = num_rendered
         ctx.set_materialize_grads(False)  # unused outputs arrive as None -> NULL (= zeros) instead of zero-filled tensors
@@ -440,15 +469,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(tuple(rs) + args[1:])
             try:
-                g = _backward_native(*args, needs=needs)
+                g = _backward_native(*args, needs=needs, subset=ctx.subset)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise ex
         else:
-            g = _backward_native(*args, needs=needs)
+            g = _backward_native(*args, needs=needs, subset=ctx.subset)
         return (g["means3D"], g["means2D"], g["sh"], g["colors_precomp"], g["segments"], g["opacities"], g["scales"], g["rotations"],
-                g["cov3Ds_precomp"], None)
+                g["cov3Ds_precomp"], None, None)
 
 
 class _RasterizeGaussiansRaw(torch.autograd.Function):
@@ -535,7 +564,10 @@ class GaussianRasterizer(nn.Module):
         return visible
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, segments=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, subset=None):
+        """As the reference (diff_gaussian_rasterization/__init__.py:194-235). `subset` (optional, not in the reference): an int32
+        CUDA tensor of strictly ascending Gaussian indices -- only those are rendered, radii has one entry per list element and
+        the gradients keep the full number of rows; replaces rendering masked copies (gaussian_renderer/__init__.py:239-268)."""
         raster_settings = self.raster_settings
 
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -560,7 +592,7 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = torch.Tensor([])
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, segments, opacities, scales, rotations, cov3D_precomp,
-                                   raster_settings)
+                                   raster_settings, subset)
 
     def forward_raw(self, xyz, means2D, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions):
         """Opt-in fused-activation entry: pass pc._xyz, pc._features_dc, pc._features_rest, pc._segment, pc._opacity,

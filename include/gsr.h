@@ -85,6 +85,13 @@ typedef struct GsrGaussians {
      *   needs `opacities` (raw) as well. cov3D_precomp must be NULL. raw_params == 0: classic behaviour, shs_rest ignored. */
     const float* shs_rest;
     int32_t raw_params;
+    /* Index-list rendering: subset != NULL renders only the Gaussians subset[0..subset_count) -- row numbers
+     * into the P-row tensors above, STRICTLY ASCENDING -- without materialising masked copies of every tensor (the viewer's
+     * bbox mask, gaussian_renderer/__init__.py:239-268, and sub-scene selection). Per-Gaussian outputs (radii) then have
+     * subset_count entries, in list order; gradients stay P rows (rows outside the list are zero). State buffers are sized by
+     * subset_count. Not combined with gsr_backward_packets. */
+    const int32_t* subset;
+    int32_t subset_count;
 } GsrGaussians;
 
 /* Forward outputs; every element is written by the kernels (no pre-zeroing needed) when P > 0. */

@@ -267,3 +267,30 @@ def test_ply_checkpoint_layout_and_round_trip(tmp_path):
     assert h["features_rest"].shape == (2, 15, 3) and float(h["features_rest"][0, 2, 1]) == 9.0 + 17.0
     assert float(h["opacities"][1, 0]) == 154.0 and h["segments"][0].tolist() == [55.0, 56.0]
     assert h["scales"][0].tolist() == [57.0, 58.0, 59.0] and h["rotations"][0].tolist() == [60.0, 61.0, 62.0, 63.0]
+
+
+def test_host_helpers_match_reference_python_fixture():
+    """tests/golden/pyref_train.npz (made by importing the reference's utils/general_utils.py): the xyz learning-rate schedule,
+    the reset_opacity formula and build_rotation, all host-side / device-agnostic code of trainer.py and optim.py."""
+    import importlib
+
+    import numpy as np
+    import torch
+
+    import helpers as H
+
+    H.pkg()
+    trainer = importlib.import_module(H.PKG_NAME + ".trainer")
+    optim = importlib.import_module(H.PKG_NAME + ".optim")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pyref_train.npz"))
+    sched = trainer.get_expon_lr_func(0.00008 * 3.7, 0.0000016 * 3.7, lr_delay_mult=0.01, max_steps=30_000)
+    got = np.array([sched(int(t)) for t in z["lr_steps"]])
+    assert np.array_equal(got, z["lr_values"])  # same numpy expressions: identical doubles
+    x = torch.from_numpy(z["invsig_in"])
+    y = torch.min(x, torch.ones_like(x) * 0.01)
+    assert torch.equal(torch.log(y / (1 - y)), torch.from_numpy(z["invsig_out"]))  # NativeTrainer.reset_opacity
+    R = optim.build_rotation(torch.from_numpy(z["rot_q"]))
+    assert torch.equal(R, torch.from_numpy(z["rot_R"]))
+    o = trainer.OptimizationParams()
+    assert (o.position_lr_init, o.feature_lr, o.opacity_lr, o.segment_lr, o.scaling_lr, o.rotation_lr) == (0.00008, 0.0025, 0.05, 0.05, 0.002, 0.001)
+    assert (o.densification_interval, o.opacity_reset_interval, o.densify_from_iter, o.densify_until_iter) == (100, 3000, 500, 15_000)

@@ -67,3 +67,22 @@ def test_l1_ssim_identical_images():
     assert float(grad.abs().max()) <= 1e-6
     with pytest.raises(RuntimeError, match="no CPU path"):
         losses.l1_ssim_loss_and_grad(img.cpu(), img.cpu())
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_l1_ssim_matches_reference_python_fixture(tag):
+    """tests/golden/pyref_train.npz: loss, L1, SSIM and dloss/dimage produced by IMPORTING the reference's utils/loss_utils.py
+    (l1_loss, ssim) and combining them as train.py:110-111 does, on CPU (tests/golden/make_golden_pyref_train.py)."""
+    import os
+
+    import numpy as np
+
+    H.pkg()
+    losses = importlib.import_module(H.PKG_NAME + ".losses")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyref_train.npz"))
+    img, gt = torch.from_numpy(z["loss_%s_img" % tag]).cuda(), torch.from_numpy(z["loss_%s_gt" % tag]).cuda()
+    stats, grad = losses.l1_ssim_loss_and_grad(img, gt, 0.2)
+    want = z["loss_%s_stats" % tag]
+    for i in range(3):
+        assert abs(float(stats[i]) - want[i]) <= 1e-5, (i, float(stats[i]), want[i])
+    assert H.rel_linf(grad, torch.from_numpy(z["loss_%s_grad" % tag]).cuda()) <= 1e-4

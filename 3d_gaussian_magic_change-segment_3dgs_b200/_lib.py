@@ -21,13 +21,23 @@ class GsrView(ctypes.Structure):
 
 
 class GsrGaussians(ctypes.Structure):
-    _fields_ = [
+    pass
+
+
+GsrGaussians._fields_ = [
         ("P", ctypes.c_int32),
         ("means3D", ctypes.c_void_p), ("shs", ctypes.c_void_p), ("colors_precomp", ctypes.c_void_p), ("segments", ctypes.c_void_p),
         ("opacities", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p), ("cov3D_precomp", ctypes.c_void_p),
         ("shs_rest", ctypes.c_void_p), ("raw_params", ctypes.c_int32),
         ("subset", ctypes.c_void_p), ("subset_count", ctypes.c_int32),
-    ]
+        ("parts", ctypes.POINTER(GsrGaussians)), ("num_parts", ctypes.c_int32),
+]
+GSR_MAX_PARTS = 16
+
+
+class GsrMicrobench(ctypes.Structure):
+    _fields_ = [("ffma_tflops", ctypes.c_float), ("ffma2_tflops", ctypes.c_float), ("ex2_gops", ctypes.c_float), ("shfl_gops", ctypes.c_float),
+                ("red_gops", ctypes.c_float), ("sm_clock_mhz_nominal", ctypes.c_float), ("sm_count", ctypes.c_int32)]
 
 
 class GsrOutputs(ctypes.Structure):
@@ -36,7 +46,8 @@ class GsrOutputs(ctypes.Structure):
 
 
 class GsrState(ctypes.Structure):
-    _fields_ = [("geom", ctypes.c_void_p), ("binning", ctypes.c_void_p), ("img", ctypes.c_void_p), ("num_rendered", ctypes.c_int32)]
+    _fields_ = [("geom", ctypes.c_void_p), ("binning", ctypes.c_void_p), ("img", ctypes.c_void_p), ("num_rendered", ctypes.c_int32),
+                ("num_visible", ctypes.c_int32)]
 
 
 class GsrPixelGrads(ctypes.Structure):
@@ -57,7 +68,7 @@ class GsrStateExport(ctypes.Structure):
 
 
 class GsrAdamGroup(ctypes.Structure):
-    _fields_ = [("offset", ctypes.c_uint64), ("count", ctypes.c_uint64), ("lr", ctypes.c_float)]
+    _fields_ = [("offset", ctypes.c_uint64), ("count", ctypes.c_uint64), ("lr", ctypes.c_float), ("step", ctypes.c_int32)]
 
 
 ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t)
@@ -66,8 +77,8 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
            "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
-           "gsr_peer_free", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible"]
-GSR_ABI_VERSION = 2  # include/gsr.h
+           "gsr_peer_free", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible", "gsr_microbench", "gsr_count_work"]
+GSR_ABI_VERSION = 3  # include/gsr.h
 GSR_PACKET_WORDS = 17
 GSR_PEER_HANDLE_BYTES = 64
 GSR_MAX_GATHER_VIEWS = 64
@@ -145,6 +156,10 @@ def lib():
     L.gsr_export_state.restype = ctypes.c_int
     L.gsr_export_state.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(GsrState), ctypes.POINTER(GsrStateExport),
                                    ctypes.c_void_p]
+    L.gsr_microbench.restype = ctypes.c_int
+    L.gsr_microbench.argtypes = [ctypes.POINTER(GsrMicrobench), ctypes.c_void_p]
+    L.gsr_count_work.restype = ctypes.c_int
+    L.gsr_count_work.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(GsrState), ctypes.c_void_p, ctypes.c_void_p]
     L.gsr_launch_count.restype = ctypes.c_ulonglong
     L.gsr_set_profiling.restype = None
     L.gsr_set_profiling.argtypes = [ctypes.c_int]

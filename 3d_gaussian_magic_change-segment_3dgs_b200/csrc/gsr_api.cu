@@ -110,6 +110,7 @@ struct SideStream
 {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr; // profiling mode: the fills' own duration on the side stream
 };
 static SideStream* side_stream()
 {
@@ -121,6 +122,7 @@ static SideStream* side_stream()
         if (check_cuda(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
         if (check_cuda(cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
         if (check_cuda(cudaEventCreateWithFlags(&h.join, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+        if (check_cuda(cudaEventCreate(&h.t0), "cudaEventCreate") || check_cuda(cudaEventCreate(&h.t1), "cudaEventCreate")) return nullptr;
     }
     return &h;
 }
@@ -130,6 +132,53 @@ static int ceil_log2(uint32_t v)
     int b = 0;
     while (b < 32 && (1ull << b) < v) b++;
     return b;
+}
+
+// Fused sub-scenes (GsrGaussians.parts): check the part list and return, in `eff`, the Gaussians struct the rest of the host
+// code reasons about (which optional members exist) -- the caller's own struct, or part 0's pointers with the fused P.
+static int resolve_parts(const GsrGaussians* in, GsrGaussians& eff)
+{
+    eff = *in;
+    if (in->num_parts <= 0) {
+        eff.num_parts = 0;
+        eff.parts = nullptr;
+        return 0;
+    }
+    if (in->num_parts > GSR_MAX_PARTS || !in->parts) {
+        set_error("num_parts=%d: at most %d parts, and `parts` must be set", in->num_parts, GSR_MAX_PARTS);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (in->raw_params || in->subset) {
+        set_error("fused sub-scenes (parts) are not combined with raw_params or subset");
+        return GSR_ERR_UNSUPPORTED;
+    }
+    long long total = 0;
+    const GsrGaussians& p0 = in->parts[0];
+    for (int k = 0; k < in->num_parts; k++) {
+        const GsrGaussians& pk = in->parts[k];
+        if (pk.P <= 0 || pk.num_parts > 0 || pk.subset || pk.raw_params) {
+            set_error("part %d: P must be > 0 and parts do not nest / carry subset / raw_params", k);
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+        const bool same = (pk.means3D != nullptr) == (p0.means3D != nullptr) && (pk.shs != nullptr) == (p0.shs != nullptr) &&
+                          (pk.colors_precomp != nullptr) == (p0.colors_precomp != nullptr) && (pk.segments != nullptr) == (p0.segments != nullptr) &&
+                          (pk.opacities != nullptr) == (p0.opacities != nullptr) && (pk.scales != nullptr) == (p0.scales != nullptr) &&
+                          (pk.rotations != nullptr) == (p0.rotations != nullptr) && (pk.cov3D_precomp != nullptr) == (p0.cov3D_precomp != nullptr);
+        if (!same) {
+            set_error("part %d provides a different set of members than part 0", k);
+            return GSR_ERR_INVALID_ARGUMENT;
+        }
+        total += pk.P;
+    }
+    if (total != (long long)in->P) {
+        set_error("P=%d is not the sum of the parts' sizes (%lld)", in->P, total);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    eff = p0;
+    eff.P = in->P;
+    eff.parts = in->parts;
+    eff.num_parts = in->num_parts;
+    return 0;
 }
 
 static int validate(const GsrView* view, const GsrGaussians* in)
@@ -209,11 +258,19 @@ extern "C" int gsr_get_stage_times(float* ms, const char** names)
     return g_timer.count;
 }
 
-extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const GsrOutputs* out, gsr_alloc_fn alloc, void* alloc_user,
+extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const GsrOutputs* out, gsr_alloc_fn alloc, void* alloc_user,
                            int32_t* num_rendered, gsr_stream_t stream_)
 {
     cudaStream_t s = (cudaStream_t)stream_;
-    int rc = validate(view, in);
+    if (!view || !in_) {
+        set_error("null view/gaussians");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    GsrGaussians eff;
+    int rc = resolve_parts(in_, eff);
+    if (rc) return rc;
+    const GsrGaussians* in = &eff;
+    rc = validate(view, in);
     if (rc) return rc;
     if (num_rendered) *num_rendered = 0;
     if (in->P == 0 || (in->subset && in->subset_count == 0)) return 0;
@@ -261,6 +318,13 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in, const Gs
     pa.focal_y = H / (2.0f * view->tanfovy); // rasterizer_impl.cu:226-227
     pa.focal_x = W / (2.0f * view->tanfovx);
     pa.grid_x = gx; pa.grid_y = gy; pa.prefiltered = view->prefiltered; pa.radii = out->radii; pa.g = g;
+    pa.num_parts = in->num_parts;
+    pa.part_start[0] = 0;
+    for (int k = 0; k < in->num_parts; k++) {
+        const GsrGaussians& pk = in->parts[k];
+        pa.part[k] = {pk.means3D, pk.scales, pk.rotations, pk.opacities, pk.shs, pk.cov3D_precomp, pk.colors_precomp, pk.segments};
+        pa.part_start[k + 1] = pa.part_start[k] + pk.P;
+    }
     launch_preprocess_fwd(pa, s);
     GSR_LAUNCHED(s, debug, "preprocess_fwd");
     launch_block_offsets(g, s);
@@ -382,6 +446,10 @@ extern "C" int gsr_backward_packets(const GsrView* view, const GsrGaussians* in,
         set_error("gsr_backward_packets needs shs and scales/rotations");
         return GSR_ERR_UNSUPPORTED;
     }
+    if (state && state->num_visible > 0 && (uint32_t)state->num_visible > capacity) {
+        set_error("gsr_backward_packets: %d visible Gaussians do not fit %u packets", state->num_visible, capacity);
+        return GSR_ERR_OVERFLOW;
+    }
     GsrParamGrads g;
     memset(&g, 0, sizeof(g));
     g.dL_dmeans2D = dL_dmeans2D;
@@ -496,6 +564,10 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
                          const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, cudaStream_t s,
                          uint32_t* packets, uint32_t capacity, uint32_t* count_dev, uint32_t* vis_index)
 {
+    if (in && in->num_parts > 0) {
+        set_error("gsr_backward: fused sub-scenes (parts) are render-only");
+        return GSR_ERR_UNSUPPORTED;
+    }
     int rc = validate(view, in);
     if (rc) return rc;
     if (in->P == 0 || (in->subset && in->subset_count == 0)) return 0;
@@ -553,8 +625,10 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     if (!ss) return GSR_ERR_CUDA;
     GSR_CUDA(cudaEventRecord(ss->fork, s));
     GSR_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t0, ss->stream));
     rc = launch_grad_fills(pb, ss->stream);
     if (rc) return rc;
+    if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t1, ss->stream));
     GSR_CUDA(cudaEventRecord(ss->join, ss->stream));
 
     GSR_CUDA(cudaMemsetAsync(grad_rec, 0, (size_t)g.slots * GRAD_REC_FLOATS * sizeof(float), s));
@@ -575,6 +649,16 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     GSR_LAUNCHED(s, debug, "preprocess_bwd");
     g_timer.mark(s, "preprocess_bwd");
     g_timer.finish(s, kBwdFirstSlot);
+    if (g_timer.enabled && g_timer.count < GSR_STAGE_COUNT) { // the stream was synchronised by finish(): the side stream's events are done
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ss->t0, ss->t1) == cudaSuccess) {
+            g_timer.ms[g_timer.count] = t;
+            g_timer.out_names[g_timer.count] = "grad_fills";
+            g_timer.count++;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     return 0;
 }
 

@@ -141,6 +141,18 @@ void count_launches(int n); // kernels launched by this library (gsr_launch_coun
     } while (0)
 
 // ---- launch-side argument blocks ----
+struct PartPtrs // one sub-scene of a fused scene (GsrGaussians.parts)
+{
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* colors_precomp;
+    const float* segments;
+};
+
 struct PreFwdArgs
 {
     int P, D, M, S;
@@ -165,6 +177,9 @@ struct PreFwdArgs
     int prefiltered;
     int32_t* radii;
     GeomState g;
+    int num_parts;                      // > 0: Gaussian idx lives in part k with part_start[k] <= idx < part_start[k + 1]
+    int part_start[GSR_MAX_PARTS + 1];
+    PartPtrs part[GSR_MAX_PARTS];
 };
 
 struct PreBwdArgs

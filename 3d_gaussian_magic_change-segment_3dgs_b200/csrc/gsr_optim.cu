@@ -31,18 +31,19 @@ struct AdamArgs
     unsigned long long offset[ADAM_MAX_GROUPS];
     unsigned long long count[ADAM_MAX_GROUPS];
     unsigned int first_chunk[ADAM_MAX_GROUPS + 1]; // CTA -> group table
-    float neg_step_size[ADAM_MAX_GROUPS];          // -(lr / bias_correction1)
-    float w1, b2, w2, bc2_sqrt, eps;               // 1-b1, b2, 1-b2, sqrt(1-b2^t), eps
+    float neg_step_size[ADAM_MAX_GROUPS];          // -(lr / bias_correction1), per group (each group has its own step count)
+    float bc2_sqrt[ADAM_MAX_GROUPS];               // sqrt(1 - b2^t), per group
+    float w1, b2, w2, eps;                         // 1-b1, b2, 1-b2, eps
 };
 
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float nss)
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float nss, float bc2_sqrt)
 {
     m = __fmaf_rn(a.w1, g - m, m);
     v = __fmaf_rn(a.w2, g * g, v * a.b2);
     // m == 0 (a Gaussian no view has seen yet): torch adds -step * (0 / d) = 0, p keeps its bits. Skipping it also skips the
     // special-operand slow paths of the IEEE sqrt and divisions, which otherwise cost 1.8x on a step where 80 % of the rows are zero.
     if (m != 0.f) {
-        const float d = sqrtf(v) / a.bc2_sqrt + a.eps;
+        const float d = sqrtf(v) / bc2_sqrt + a.eps;
         p = __fmaf_rn(nss, m / d, p);
     }
 }
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a)
     while (grp + 1 < a.num_groups && blockIdx.x >= a.first_chunk[grp + 1]) grp++;
     const unsigned long long base = a.offset[grp], n = a.count[grp];
     const unsigned long long c0 = (unsigned long long)(blockIdx.x - a.first_chunk[grp]) * ADAM_CHUNK;
-    const float nss = a.neg_step_size[grp];
+    const float nss = a.neg_step_size[grp], bcs = a.bc2_sqrt[grp];
     float* p = a.p + base;
     const float* g = a.g + base;
     float* m = a.m + base;
@@ -81,10 +82,10 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a)
         }
 #pragma unroll
         for (int t = 0; t < TRIPS; t++) {
-            adam_one(P4[t].x, G4[t].x, M4[t].x, V4[t].x, a, nss);
-            adam_one(P4[t].y, G4[t].y, M4[t].y, V4[t].y, a, nss);
-            adam_one(P4[t].z, G4[t].z, M4[t].z, V4[t].z, a, nss);
-            adam_one(P4[t].w, G4[t].w, M4[t].w, V4[t].w, a, nss);
+            adam_one(P4[t].x, G4[t].x, M4[t].x, V4[t].x, a, nss, bcs);
+            adam_one(P4[t].y, G4[t].y, M4[t].y, V4[t].y, a, nss, bcs);
+            adam_one(P4[t].z, G4[t].z, M4[t].z, V4[t].z, a, nss, bcs);
+            adam_one(P4[t].w, G4[t].w, M4[t].w, V4[t].w, a, nss, bcs);
             const unsigned long long i = c0 + (unsigned long long)(t * ADAM_THREADS + threadIdx.x) * ADAM_VEC;
             if (STREAM) {
                 __stcs(reinterpret_cast<float4*>(p + i), P4[t]);
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const AdamArgs a)
     }
     for (unsigned long long i = c0 + threadIdx.x; i < n && i < c0 + ADAM_CHUNK; i += ADAM_THREADS) {
         float pp = p[i], mm = m[i], vv = v[i];
-        adam_one(pp, g[i], mm, vv, a, nss);
+        adam_one(pp, g[i], mm, vv, a, nss, bcs);
         p[i] = pp;
         m[i] = mm;
         v[i] = vv;
@@ -123,14 +124,17 @@ extern "C" int gsr_adam_step(float* params, const float* grads, float* exp_avg, 
     a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.num_groups = num_groups;
     // Python: bias_correction1 = 1 - beta1 ** step; step_size = lr / bias_correction1; bias_correction2_sqrt = sqrt(1 - beta2 ** step)
     const double b1 = beta1, b2 = beta2; // doubles end to end: (float)0.9 would turn 1 - beta1 into 0.10000002
-    const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
-    a.w1 = (float)(1.0 - b1); a.b2 = (float)b2; a.w2 = (float)(1.0 - b2); a.bc2_sqrt = (float)sqrt(bc2); a.eps = (float)eps;
+    a.w1 = (float)(1.0 - b1); a.b2 = (float)b2; a.w2 = (float)(1.0 - b2); a.eps = (float)eps;
     // 4 x LDG.128 per array per thread; 1, 2 or 4 trips and evict-first hints all measure 1.47 ms (6.97 TB/s) at 61 x 6M floats
     const unsigned long long ADAM_CHUNK = (unsigned long long)ADAM_THREADS * ADAM_VEC * ADAM_TRIPS;
     unsigned long long chunks = 0;
     for (int i = 0; i < num_groups; i++) {
         a.offset[i] = groups[i].offset; a.count[i] = groups[i].count;
+        // torch.optim.Adam keeps `step` per parameter: a group that skipped steps (its tensor was just replaced) lags behind
+        const double t = (double)(groups[i].step > 0 ? groups[i].step : step);
+        const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
         a.neg_step_size[i] = (float)(-((double)groups[i].lr / bc1));
+        a.bc2_sqrt[i] = (float)sqrt(bc2);
         a.first_chunk[i] = (unsigned int)chunks;
         chunks += (groups[i].count + ADAM_CHUNK - 1) / ADAM_CHUNK;
     }
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rows_kernel(const SelectAr
     int k = 0;
 #pragma unroll 1
     while (k + 1 < a.num_blocks && blockIdx.x >= a.first_chunk[k + 1]) k++;
-    const unsigned rf = (unsigned)a.row[k];
+    const unsigned rf = (unsigned)a.row[k]; // > 0: zero-width blocks (features_rest at SH degree 0) own no CTA
     const unsigned long long n = (unsigned long long)a.n_out * rf;
     const unsigned long long c0 = (unsigned long long)(blockIdx.x - a.first_chunk[k]) * SEL_CHUNK;
     const float* src = a.src + a.src_off[k];
@@ -209,14 +213,15 @@ extern "C" int gsr_select_rows(const float* src, float* dst, const int64_t* inde
     a.src = src; a.dst = dst; a.index = (const long long*)index; a.n_out = n_out; a.n_src = n_src; a.num_blocks = num_blocks;
     unsigned long long chunks = 0;
     for (int k = 0; k < num_blocks; k++) {
-        if (row_floats[k] <= 0) {
-            set_error("gsr_select_rows: row_floats[%d] must be positive", k);
+        if (row_floats[k] < 0) {
+            set_error("gsr_select_rows: row_floats[%d] must not be negative", k);
             return GSR_ERR_INVALID_ARGUMENT;
         }
         a.row[k] = row_floats[k]; a.src_off[k] = src_offsets[k]; a.dst_off[k] = dst_offsets[k]; a.first_chunk[k] = (unsigned int)chunks;
         chunks += ((unsigned long long)row_floats[k] * (unsigned long long)n_out + SEL_CHUNK - 1) / SEL_CHUNK;
     }
     a.first_chunk[num_blocks] = (unsigned int)chunks;
+    if (chunks == 0) return 0;
     if (chunks > 0x7fffffffull) {
         set_error("gsr_select_rows: too many rows");
         return GSR_ERR_UNSUPPORTED;

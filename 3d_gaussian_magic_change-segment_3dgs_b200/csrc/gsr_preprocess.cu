@@ -54,8 +54,15 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
 
     int gid = idx; // row of the input tensors: the position itself, or the list entry when an index list is rendered
     if (idx < a.P) {
+        PartPtrs in = {a.means3D, a.scales, a.rotations, a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp, a.segments};
         if (a.subset) gid = a.subset[idx];
-        const float3 p_orig = {a.means3D[3 * gid], a.means3D[3 * gid + 1], a.means3D[3 * gid + 2]};
+        if (a.num_parts > 0) { // fused sub-scenes: this Gaussian's part and its row there (a CTA may straddle a boundary)
+            int k = 0;
+            while (k + 1 < a.num_parts && idx >= a.part_start[k + 1]) k++;
+            in = a.part[k];
+            gid = idx - a.part_start[k];
+        }
+        const float3 p_orig = {in.means3D[3 * gid], in.means3D[3 * gid + 1], in.means3D[3 * gid + 2]};
         // near cull (auxiliary.h:139-164); the +-1.3 NDC test is disabled in the reference
         const float4 p_hom = xform_point_h(p_orig, s_proj);
         const float p_w = 1.0f / (p_hom.w + 0.0000001f);
@@ -65,12 +72,12 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
             filtered = a.prefiltered != 0;
         } else {
             float cov3D[6];
-            if (a.cov3D_precomp != nullptr) {
+            if (in.cov3D_precomp != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) cov3D[i] = a.cov3D_precomp[6 * (size_t)gid + i];
+                for (int i = 0; i < 6; i++) cov3D[i] = in.cov3D_precomp[6 * (size_t)gid + i];
             } else {
-                float3 sc = {a.scales[3 * gid], a.scales[3 * gid + 1], a.scales[3 * gid + 2]};
-                float4 q = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)gid);
+                float3 sc = {in.scales[3 * gid], in.scales[3 * gid + 1], in.scales[3 * gid + 2]};
+                float4 q = *reinterpret_cast<const float4*>(in.rotations + 4 * (size_t)gid);
                 if (a.raw) { // fused activations (scene/gaussian_model.py:100-106): exp, normalize
                     sc = {expf(sc.x), expf(sc.y), expf(sc.z)};
                     q = act_normalize(q);
@@ -92,22 +99,22 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
                 if ((rmax.x - rmin.x) * (rmax.y - rmin.y) != 0) {
                     visible = true;
                     float3 rgb;
-                    if (a.colors_precomp == nullptr) {
+                    if (in.colors_precomp == nullptr) {
                         const float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
-                        const float3* sh3 = reinterpret_cast<const float3*>(a.shs);
+                        const float3* sh3 = reinterpret_cast<const float3*>(in.shs);
                         const ShCoeffs<float3> sh = a.raw ? ShCoeffs<float3>{sh3 + gid, reinterpret_cast<const float3*>(a.shs_rest) + (size_t)gid * (a.M - 1)}
                                                           : ShCoeffs<float3>{sh3 + (size_t)gid * a.M, sh3 + (size_t)gid * a.M + 1};
                         rgb = sh_to_rgb(a.D, p_orig, campos, sh, clamp_bits);
                     } else {
-                        rgb = {a.colors_precomp[3 * gid], a.colors_precomp[3 * gid + 1], a.colors_precomp[3 * gid + 2]};
+                        rgb = {in.colors_precomp[3 * gid], in.colors_precomp[3 * gid + 1], in.colors_precomp[3 * gid + 2]};
                     }
                     float s0 = 0.f, s1 = 0.f;
-                    if (a.S == 2 && a.segments != nullptr) {
-                        const float2 sg = *reinterpret_cast<const float2*>(a.segments + 2 * (size_t)gid);
+                    if (a.S == 2 && in.segments != nullptr) {
+                        const float2 sg = *reinterpret_cast<const float2*>(in.segments + 2 * (size_t)gid);
                         s0 = a.raw ? act_sigmoid(sg.x) : sg.x;
                         s1 = a.raw ? act_sigmoid(sg.y) : sg.y;
                     }
-                    const float op = a.raw ? act_sigmoid(a.opacities[gid]) : a.opacities[gid];
+                    const float op = a.raw ? act_sigmoid(in.opacities[gid]) : in.opacities[gid];
                     radius_out = my_radius;
                     A = {point_image.x, point_image.y, conic.x, conic.y};
                     B = {conic.z, op, rgb.x, rgb.y};
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
         a.g.rec[3 * (size_t)slot + 1] = B;
         a.g.rec[3 * (size_t)slot + 2] = C;
         a.g.rect[slot] = rect;
-        a.g.slot_gid[slot] = (uint32_t)gid; // the backward addresses inputs and gradient rows through this
+        a.g.slot_gid[slot] = (uint32_t)(a.num_parts > 0 ? idx : gid); // the backward addresses inputs and gradient rows through this
         a.g.clamped[slot] = (uint8_t)clamp_bits;
     }
     // instance count of the block -> global R (integer atomics: deterministic total)

@@ -42,6 +42,7 @@ _lib = _load_lib_module()
 ALLOC_FN, GsrGaussians, GsrOutputs, GsrParamGrads = _lib.ALLOC_FN, _lib.GsrGaussians, _lib.GsrOutputs, _lib.GsrParamGrads
 GsrPixelGrads, GsrState, GsrStateExport, GsrView = _lib.GsrPixelGrads, _lib.GsrState, _lib.GsrStateExport, _lib.GsrView
 
+PACKET_WORDS = _lib.GSR_PACKET_WORDS
 NUM_CHANNELS = 3  # cuda_rasterizer/config.h:15
 NUM_CLASS = 2     # cuda_rasterizer/config.h:16 (segment channels rendered when `segments` is absent)
 
@@ -59,14 +60,30 @@ def _ptr(t):
 
 
 def _prep(t, device, what):
-    """contiguous fp32 on the compute device (the reference calls .contiguous().data<float>())."""
+    """contiguous fp32 on the compute device (the reference calls .contiguous().data<float>()), starting on a 16-byte boundary:
+    the kernels load quaternions as float4 and segments as float2, so a contiguous VIEW at an odd offset of a larger buffer
+    (which the reference's scalar loads accept) is copied once instead of faulting."""
     if t is None or t.numel() == 0:
         return None
     if t.device != device:
         raise RuntimeError("%s must be on %s (got %s); libgsr has no CPU path" % (what, device, t.device))
     if t.dtype != torch.float32:
         raise RuntimeError("%s must be float32 (got %s)" % (what, t.dtype))
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+class NumRendered(int):
+    """The forward's num_rendered (a plain int for every consumer, as in the reference) that also remembers how many Gaussians
+    THAT forward found visible -- what sizes the packet buffer of that view's backward, whatever ran on the thread in between."""
+    num_visible = 0
+
+    def __new__(cls, rendered, visible):
+        obj = super().__new__(cls, rendered)
+        obj.num_visible = int(visible)
+        return obj
 
 
 class _Alloc:
@@ -180,6 +197,87 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
         return R.value, color, depth, segment, alpha, radii, e(bufs[0]), e(bufs[1]), e(bufs[2])
 
 
+def _forward_parts_native(parts, rs):
+    """Sub-scene fusion without concatenation (GsrGaussians.parts; the viewer's _merge_scenes, visualizer.py:196-226, concatenates
+    every attribute array of the sub-scenes instead). `parts`: list of dicts with the classic inputs of one sub-scene each --
+    means3D, opacities, and shs | colors_precomp, scales + rotations | cov3D_precomp, optionally segments -- all providing the same
+    members. Renders them as ONE scene (part 0's Gaussians first) and returns the 9-tuple of _forward_native; radii covers the
+    fused scene. Render-only: there is no backward for this entry."""
+    if not parts or len(parts) > _lib.GSR_MAX_PARTS:
+        raise RuntimeError("forward_parts needs 1..%d sub-scenes" % _lib.GSR_MAX_PARTS)
+    L = _lib.lib()
+    device = parts[0]["means3D"].device
+    if not parts[0]["means3D"].is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor; libgsr has no CPU path")
+    H, W = int(rs.image_height), int(rs.image_width)
+    keys = ["means3D", "shs", "colors_precomp", "segments", "opacities", "scales", "rotations", "cov3D_precomp"]
+    have0 = [k for k in keys if parts[0].get(k) is not None and parts[0][k].numel() > 0]
+    with torch.cuda.device(device):
+        arr = (GsrGaussians * len(parts))()
+        keep, total = [], 0
+        for i, part in enumerate(parts):
+            if [k for k in keys if part.get(k) is not None and part[k].numel() > 0] != have0:
+                raise RuntimeError("sub-scene %d provides a different set of inputs than sub-scene 0" % i)
+            if part["means3D"].dim() != 2 or part["means3D"].size(1) != 3 or part["means3D"].size(0) == 0:
+                raise RuntimeError("means3D must have dimensions (num_points > 0, 3)")
+            t = {k: _prep(part.get(k), device, k) for k in keys}
+            keep.append(t)
+            n = t["means3D"].size(0)
+            arr[i] = GsrGaussians(n, _ptr(t["means3D"]), _ptr(t["shs"]), _ptr(t["colors_precomp"]), _ptr(t["segments"]), _ptr(t["opacities"]),
+                                  _ptr(t["scales"]), _ptr(t["rotations"]), _ptr(t["cov3D_precomp"]), None, 0, None, 0, None, 0)
+            total += n
+        first = keep[0]
+        M = first["shs"].size(1) if first["shs"] is not None else 0
+        num_class = first["segments"].size(1) if first["segments"] is not None else NUM_CLASS
+        k2 = {"device": device}
+        view = _view_struct(rs, M, num_class, k2)
+        gin = GsrGaussians(total, None, None, None, None, None, None, None, None, None, 0, None, 0, arr, len(parts))
+        opts = dict(dtype=torch.float32, device=device)
+        color, segment = torch.empty((NUM_CHANNELS, H, W), **opts), torch.empty((num_class, H, W), **opts)
+        depth, alpha = torch.empty((1, H, W), **opts), torch.empty((1, H, W), **opts)
+        radii = torch.empty(total, dtype=torch.int32, device=device)
+        out = GsrOutputs(color.data_ptr(), segment.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii.data_ptr())
+        alloc = _Alloc(device)
+        R = ctypes.c_int32(0)
+        try:
+            rc = L.gsr_forward(ctypes.byref(view), ctypes.byref(gin), ctypes.byref(out), alloc.cb, None, ctypes.byref(R),
+                               torch.cuda.current_stream(device).cuda_stream)
+            bufs = alloc.bufs
+        finally:
+            alloc.release()
+        _lib.check(rc, "gsr_forward")
+        e = lambda t: t if t is not None else torch.empty(0, dtype=torch.uint8, device=device)
+        return R.value, color, depth, segment, alpha, radii, e(bufs[0]), e(bufs[1]), e(bufs[2])
+
+
+def count_work(P, W, H, geomBuffer, binningBuffer, imgBuffer, num_rendered):
+    """gsr_count_work: algorithmic work of a rendered frame counted from its saved state (measurement support):
+    {"E": entries evaluated front to back, "Cc": contributing entries, "E_b": entries the backward re-traverses}."""
+    L = _lib.lib()
+    device = geomBuffer.device
+    with torch.cuda.device(device):
+        cnt = torch.zeros(3, dtype=torch.int64, device=device)
+        st = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
+        rc = L.gsr_count_work(int(P), int(W), int(H), ctypes.byref(st), cnt.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "gsr_count_work")
+        E, Cc, Eb = (int(v) for v in cnt.tolist())
+    return {"E": E, "Cc": Cc, "E_b": Eb}
+
+
+def microbench(device=None):
+    """gsr_microbench on the current (or given) device: achievable FFMA / FFMA2 / MUFU.EX2 / SHFL / red.global rates (dict)."""
+    L = _lib.lib()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    with torch.cuda.device(device):
+        r = _lib.GsrMicrobench()
+        _lib.check(L.gsr_microbench(ctypes.byref(r), torch.cuda.current_stream(device).cuda_stream), "gsr_microbench")
+    return {"ffma_tflops": round(r.ffma_tflops, 3), "ffma2_tflops": round(r.ffma2_tflops, 3), "ex2_gops": round(r.ex2_gops, 2),
+            "shfl_gops": round(r.shfl_gops, 2), "red_gops": round(r.red_gops, 3), "sm_count": int(r.sm_count),
+            "sm_clock_mhz_nominal": round(r.sm_clock_mhz_nominal, 1),
+            "what": "dependent-chain-free FFMA (3-register form), packed FFMA2, MUFU.EX2, SHFL (lane-ops/s) and 12-lane red.global.add.f32 "
+                    "into 48-byte records of an L2-resident table (float atomics/s), CUDA events, 64 warps/SM"}
+
+
 def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotations, cov3Ds_precomp, grad_color, grad_segment, grad_depth,
                      grad_alpha, sh, geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, needs=None, out=None, accumulate=False,
                      sh_rest=None, raw_params=False, opacities=None, subset=None):
@@ -256,7 +354,7 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
         pg = GsrParamGrads(_ptr(grads["means3D"]), _ptr(grads["means2D"]), _ptr(grads["sh"]), _ptr(grads["colors_precomp"]),
                            _ptr(grads["segments"]), _ptr(grads["opacities"]), _ptr(grads["scales"]), _ptr(grads["rotations"]),
                            _ptr(grads["cov3Ds_precomp"]), int(bool(accumulate)), _ptr(grads["sh_rest"]))
-        state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
+        state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered), int(getattr(num_rendered, "num_visible", 0)))
         nscratch = L.gsr_backward_scratch_bytes(count)
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
         t_radii = radii.contiguous()
@@ -301,7 +399,7 @@ def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, gr
             g_col = torch.zeros((NUM_CHANNELS, H, W), **opts)
         g_seg, g_dep, g_alp = _prep(grad_segment, device, "grad_segment"), _prep(grad_depth, device, "grad_depth"), _prep(grad_alpha, device, "grad_alpha")
         pix = GsrPixelGrads(g_col.data_ptr(), _ptr(g_seg), _ptr(g_dep), _ptr(g_alp))
-        state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered))
+        state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered), int(getattr(num_rendered, "num_visible", 0)))
         nscratch = L.gsr_backward_scratch_bytes(P)
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
         cap = max(int(capacity), 1)
@@ -593,6 +691,15 @@ class GaussianRasterizer(nn.Module):
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, segments, opacities, scales, rotations, cov3D_precomp,
                                    raster_settings, subset)
+
+    def forward_parts(self, parts):
+        """Render several resident sub-scenes as ONE scene without concatenating their tensors (the viewer's scene fusion,
+        visualizer.py:196-226 / render.py:36). `parts`: list of dicts {means3D, opacities, shs | colors_precomp, scales + rotations |
+        cov3D_precomp, segments}. Returns (color, radii, depth, alpha, segment) like forward(); radii covers the fused scene in
+        part order. Render-only (no gradients)."""
+        with torch.no_grad():
+            R, color, depth, segment, alpha, radii, _, _, _ = _forward_parts_native(parts, self.raster_settings)
+        return color, radii, depth, alpha, segment
 
     def forward_raw(self, xyz, means2D, features_dc, features_rest, segment_logits, opacity_logits, log_scales, quaternions):
         """Opt-in fused-activation entry: pass pc._xyz, pc._features_dc, pc._features_rest, pc._segment, pc._opacity,

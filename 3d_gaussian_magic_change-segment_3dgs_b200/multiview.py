@@ -174,7 +174,8 @@ def native_view_backward_packets(D, leaves, rs, fwd, upstream, means2D_grad=None
     visibility index, see D.packet_blob_views) with room for max(capacity, V) packets. Passing the exchange's sticky
     capacity (`state["cap"]` of exchange_packets) lets the blob be all-gathered in place, without a repacking copy."""
     R, color, depth, segment, alpha, radii, geom, binb, img = fwd
-    nvis = D.last_num_visible()
+    # V of the forward this backward belongs to (carried by its num_rendered), not of whatever forward ran last on the thread
+    nvis = int(R.num_visible) if hasattr(R, "num_visible") else int((radii > 0).sum())
     sh, raw = _sh_and_raw(leaves)
     blob, count = D._backward_packets_native(rs, leaves["means3D"], radii, leaves["segments"], leaves["scales"], leaves["rotations"],
                                              upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"),

@@ -55,7 +55,7 @@ class FusedAdam:
             raise KeyError("unknown parameter group(s): %s" % sorted(unknown))
         self.exp_avg = torch.zeros_like(params.buffer)
         self.exp_avg_sq = torch.zeros_like(params.buffer)
-        self.step_count = 0
+        self.steps = {n: 0 for n in params.shapes}  # torch.optim.Adam keeps `step` per parameter: a skipped group lags behind
 
     def set_lr(self, group, lr):
         """update_learning_rate (scene/gaussian_model.py:184-190) sets the xyz group's rate every iteration."""
@@ -70,12 +70,14 @@ class FusedAdam:
         names = [n for n in offs if n in self.lrs and n not in skip]
         if not names:
             return
-        self.step_count += 1
-        arr = (_lib.GsrAdamGroup * len(names))(*[_lib.GsrAdamGroup(offs[n][0], offs[n][1], self.lrs[n]) for n in names])
+        names = [n for n in names if offs[n][1] > 0]
+        for n in names:
+            self.steps[n] += 1
+        arr = (_lib.GsrAdamGroup * len(names))(*[_lib.GsrAdamGroup(offs[n][0], offs[n][1], self.lrs[n], self.steps[n]) for n in names])
         dev = self.params.buffer.device
         with torch.cuda.device(dev):
             rc = L.gsr_adam_step(self.params.buffer.data_ptr(), self.grads.buffer.data_ptr(), self.exp_avg.data_ptr(),
-                                 self.exp_avg_sq.data_ptr(), arr, len(names), self.betas[0], self.betas[1], self.eps, self.step_count,
+                                 self.exp_avg_sq.data_ptr(), arr, len(names), self.betas[0], self.betas[1], self.eps, max(self.steps.values()),
                                  torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "gsr_adam_step")
 
@@ -128,13 +130,15 @@ def build_rotation(r):
     return R
 
 
-def densify_and_prune(params, opt, xyz_gradient_accum, denom, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, N=2):
+def densify_and_prune(params, opt, xyz_gradient_accum, denom, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, N=2,
+                      generator=None):
     """GaussianModel.densify_and_prune (scene/gaussian_model.py:500-515: clone, split, prune) on the flat buffers.
 
     The masks and the handful of new rows (sampled positions, shrunk scales of split Gaussians) are computed with the same torch
     expressions as the reference on the small selected subsets -- including the one torch.normal call, so the same RNG state
     gives the same samples -- but the seven parameter tensors and their two Adam moments are rebuilt by ONE row selection each
     (gsr_select_rows) from a composed index list instead of 2 torch.cat + 2 boolean masks per tensor and state.
+    `generator`: a dedicated torch.Generator for the split samples (callers that must not disturb the global RNG stream).
     Returns (new FlatParameters, new FlatGradients, index) and re-targets `opt` (moments reindexed, fresh rows zero); the caller
     resets its densification statistics to zeros of the new size, as densification_postfix does (:443-463). Like the reference,
     the screen-size criterion sees max_radii2D AFTER that reset (all zeros), so only the world-size criterion can fire."""
@@ -160,7 +164,7 @@ def densify_and_prune(params, opt, xyz_gradient_accum, denom, max_grad, min_opac
         src_split = src1[sel_split]
         stds = scaling[src_split].repeat(N, 1)
         means = torch.zeros((stds.size(0), 3), device=dev)
-        samples = torch.normal(mean=means, std=stds)
+        samples = torch.normal(mean=means, std=stds, generator=generator)  # generator=None: the global RNG, like the reference
         rots = build_rotation(v["rotations"][src_split]).repeat(N, 1, 1)
         child_xyz = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + v["means3D"][src_split].repeat(N, 1)
         child_scale = torch.log(scaling[src_split].repeat(N, 1) / (0.8 * N))

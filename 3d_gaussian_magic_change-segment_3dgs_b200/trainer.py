@@ -67,7 +67,9 @@ class NativeTrainer:
         self.dist, self.rank, self.world = dist if world > 1 else None, rank, world
         self.device = init["means3D"].device
         self.params = optim.FlatParameters.from_tensors(init)
-        self.grads = mv.FlatGradients(self.P, self.device, split_sh=True)
+        self.grads = mv.FlatGradients(self.P, self.device, sh_coeffs=1 + init["features_rest"].size(1), num_class=init["segments"].size(1),
+                                      split_sh=True)
+        self._rng = torch.Generator(device=self.device)  # split samples of the densification: never touches the global RNG
         o = opt_params
         self.opt = optim.FusedAdam(self.params, self.grads, {"xyz": o.position_lr_init * spatial_lr_scale, "f_dc": o.feature_lr,
                                                              "f_rest": o.feature_lr / 20.0, "opacity": o.opacity_lr, "segment": o.segment_lr,
@@ -172,10 +174,10 @@ class NativeTrainer:
         """densify_and_prune with the statistics of ALL ranks; every rank draws the same samples (seeded by the iteration)."""
         if self.dist is not None:
             self.stats.allreduce(self.dist)
-        torch.manual_seed(0x3D65 + self.iteration)
+        self._rng.manual_seed(0x3D65 + self.iteration)  # the same seed on every rank: replicas draw identical samples
         self.params, self.grads, _ = optim.densify_and_prune(self.params, self.opt, self.stats.xyz_gradient_accum, self.stats.denom,
                                                              self.o.densify_grad_threshold, 0.005, self.extent, size_threshold,
-                                                             percent_dense=self.o.percent_dense)
+                                                             percent_dense=self.o.percent_dense, generator=self._rng)
         # the step's gradient was computed for the old rows; train_step skips the optimiser step of this iteration, like the
         # reference, whose rebuilt nn.Parameters carry no .grad when optimizer.step() runs (train.py:183)
         self.stats = mv.DensificationStats(self.P, self.device)

@@ -1,36 +1,49 @@
 #!/usr/bin/env python
-"""bench.py -- train-step it/s (rasterizer forward+backward, 1080p, 6M Gaussians, depth) on N B200s.
+"""bench.py -- train-step it/s (rasterizer forward+backward, 1080p, 6M Gaussians, depth) on N B200s; forward ms/frame.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1..cfg5] [--views-per-step B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of views: for each of the rank's views, rasterize_gaussians forward
-(colour + depth + alpha + segment) and backward (all parameter gradients, dense). N = 1: through the drop-in PyTorch API and
-autograd. N > 1 (multi-view data parallelism; parameters replicated, one view per rank per step): the
-gradients of all ranks' views are summed into one flat buffer on every rank -- `--grad-exchange peer` (default): each view's
-backward writes 68-byte packets of its visible Gaussians into peer-visible memory and ONE kernel per rank pulls all ranks'
-packets over NVLink while summing them (multiview.PeerPacketExchange); `packets`: the same packets through one NCCL
-all-gather; `dense`: one NCCL all-reduce of the flat buffer. Workload = BASELINE.json configs[2] ("cfg3": 6M Gaussians SH3,
-1920x1080, depth render + depth gradient), the configuration the headline metric is quoted on; synthetic seeded scene
-(synthetic.py).
+(colour + depth + alpha + segment) and backward (all parameter gradients, dense).
+
+Workloads (BASELINE.json configs, synthetic seeded scenes, `synthetic.py`):
+  cfg3 (default at N = 1)  6M Gaussians SH3, 1920x1080, depth render + depth-supervision gradient: the headline configuration.
+  cfg4 (default at N > 1)  the same scene shape, 8 views per step SHARDED over the ranks (8/N views per rank, strong scaling);
+                           `--views-per-step B` picks another batch, `--views-per-rank V` runs V views per rank (weak scaling).
+  cfg2                     3M Gaussians, 1297x840, single-view train step.        cfg1: 100k Gaussians, 800x800 (plumbing).
+  cfg5                     render-only 3840x2160, 10M Gaussians in four sub-scenes rendered through the concatenation-free
+                           multi-part entry (the viewer's scene fusion, visualizer.py:196-226); forward only, frames/s.
+N = 1 goes through the drop-in PyTorch API and autograd. N > 1 (multi-view data parallelism; parameters
+replicated): every rank's views are summed into one flat gradient buffer on every rank -- `--grad-exchange peer` (default):
+each view's backward writes compact packets of its visible Gaussians into peer-visible memory and ONE kernel per rank pulls all
+ranks' packets over NVLink while summing them; `packets`: the same packets through one NCCL all-gather; `dense`: one NCCL
+all-reduce of the flat buffer. Before the timed loop an N > 1 run executes one untimed step through `dense` and one through the
+selected exchange and reports `exchange_parity` (max relative difference of the flat buffer, and whether all ranks hold
+bit-identical buffers).
 
 Printed JSON (rank 0, one line): `value` = views/s with everything resident in HBM (CUDA events, max over ranks);
-`e2e` = the same step driven from HOST buffers: camera matrices + ground-truth image and depth copied H2D from pinned
-memory every view, L1 colour + depth loss in torch, loss scalar read back D2H; `roofline` = dominant kernel against the
-measured HBM peak; `cpu_baseline` = the C oracle (oracle/gsr_oracle.c, OpenMP) on a bounded sample of the same workload.
+`e2e` = the same step driven from HOST buffers (camera matrices + ground-truth image and depth copied H2D from pinned memory
+every view, the reference's L1 + depth-supervision loss, loss scalar read back D2H); `roofline` = the dominant kernel against
+the peak that bounds it (compositing: FP32 issue, measured by in-run micro-benchmarks; streaming stages: measured HBM copy
+bandwidth); `cpu_baseline` = the C oracle (oracle/gsr_oracle.c, OpenMP) on a bounded sample of the same workload.
 
-`--impl reference` times the reference's own CUDA rasterizer (oracle/_ref/ref_dgr_C.so, compiled from the unmodified
-sources by oracle/build_ref.py) through the same loops -- the reference ships no CPU path, so its "own implementation of
-the path" is this CUDA build; when the .so or a GPU is missing it falls back to the CPU oracle port.
+`--impl reference` times the reference's own CUDA rasterizer (oracle/_ref/ref_dgr_C.so, compiled from the unmodified sources
+by oracle/build_ref.py) through the same loops. That arm imports nothing of this repo's product (no libgsr.so): its settings
+tuple, scene generator (loaded by file path) and statistics come from the reference's own buffers. The reference ships no CPU
+path, so its "own implementation of the path" is this CUDA build; when the .so or a GPU is missing the arm falls back to the
+CPU oracle port.
 """
 import argparse
 import importlib
+import importlib.util
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+from typing import NamedTuple
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = "3d_gaussian_magic_change-segment_3dgs_b200"
@@ -40,27 +53,56 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+LEAVES = ["means3D", "shs", "segments", "opacities", "scales", "rotations"]  # 3+48+2+1+3+4 = 61 floats per Gaussian
+METRICS = {"cfg1": "train-step it/s (fwd+bwd, 800x800, 100k gaussians)", "cfg2": "train-step it/s (fwd+bwd, 1297x840, 3M gaussians)",
+           "cfg3": "train-step it/s (fwd+bwd, 1080p, 6M gaussians)", "cfg4": "train-step it/s (fwd+bwd, 1080p, 6M gaussians)",
+           "cfg5": "render frames/s (fwd only, 3840x2160, 10M gaussians)"}
+
 
 # ------------------------------------------------------------------------------------------------ clocks
-class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+R = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+while True:
+    try:
+        sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+        rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+    except Exception as e:
+        print("ERR", e, flush=True); break
+    print("%.6f,%d,%d,%.1f,%s" % (time.time(), sm, mx, pw, "|".join(k for k, b in R.items() if rs & b)), flush=True)
+    time.sleep(0.01)
+"""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+class ClockSampler:
+    """SM clock / throttle-reason sampling every 10 ms in a side PROCESS (NVML through pynvml; no GIL contention with the timed
+    loop). Falls back to `nvidia-smi -lms 20` when pynvml is unavailable."""
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.gpu, self.rows, self.proc, self.mode = gpu_index, [], None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml  # noqa: F401
+
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvml"
         except Exception:
-            self.proc = None
+            try:
+                q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.mode = "smi"
+            except Exception:
+                self.proc = None
+        if self.proc is not None:
+            threading.Thread(target=self._read, daemon=True).start()
 
     def _read(self):
         for line in self.proc.stdout:
@@ -74,33 +116,228 @@ class ClockSampler:
             except Exception:
                 pass
 
-    def summary(self, t0, t1):
+    def summary(self, windows):
+        """windows: list of (t0, t1) wall-clock intervals of the timed regions."""
         sm, mx, reasons = [], [], set()
-        for t, line in self.rows:
-            if t < t0 or t > t1 + 0.2:
-                continue
+        for t_read, line in self.rows:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
+                if self.mode == "nvml":
+                    t, s, m, rs = float(f[0]), float(f[1]), float(f[2]), [r for r in f[4].split("|") if r]
+                else:
+                    t, s, m = t_read, float(f[0]), float(f[1])
+                    rs = [n for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]) if v.lower().startswith("active")]
+            except (ValueError, IndexError):
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            if not any(a <= t <= b + 0.02 for a, b in windows):
+                continue
+            sm.append(s)
+            mx.append(m)
+            reasons.update(rs)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.mode, "period_ms": 10 if self.mode == "nvml" else 20,
+                "window": "device-timed and e2e-timed regions"}
 
 
-# ------------------------------------------------------------------------------------------------ rasterizers
-def load_ours():
-    pkg = importlib.import_module(PKG)
-    return pkg
+# ------------------------------------------------------------------------------------------------ shared plumbing (no product import)
+def load_synthetic():
+    """synthetic.py by FILE PATH: it only needs numpy/torch, and importing it through the package would load libgsr.so --
+    which the reference arm must not do."""
+    name = "_gsr_bench_synthetic"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, PKG, "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
+class RefSettings(NamedTuple):
+    """GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:168-180), defined locally for the reference arm."""
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def make_settings(cls, cam, bg, mats=None):
+    vm, pm, cp = mats if mats is not None else (cam["viewmatrix_dev"], cam["projmatrix_dev"], cam["campos_dev"])
+    return cls(image_height=cam["H"], image_width=cam["W"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg, scale_modifier=1.0,
+               viewmatrix=vm, projmatrix=pm, sh_degree=3, campos=cp, prefiltered=False, debug=False)
+
+
+def _claim_stdout():
+    """NCCL / torchrun print banners to fd 1; the contract is ONE JSON line on stdout. Park the real stdout on a private fd
+    and point fd 1 at stderr for the rest of the run."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
+def reference_depth_loss(dyn_depth, gt_depth, lambda_depth):
+    """compute_depth_loss (utils/loss_utils.py:88-102) restated in torch: the loss both arms' e2e legs use when the native
+    kernel is not the thing under test (reference arm), and the checker of the native one."""
+    dyn_depth = dyn_depth.view(1, -1)
+    gt_depth = gt_depth.view(1, -1)
+    t_d = torch.median(dyn_depth, dim=-1, keepdim=True).values
+    s_d = torch.mean(torch.abs(dyn_depth - t_d), dim=-1, keepdim=True)
+    dn = (dyn_depth - t_d) / s_d
+    t_gt = torch.median(gt_depth, dim=-1, keepdim=True).values
+    s_gt = torch.mean(torch.abs(gt_depth - t_gt), dim=-1, keepdim=True)
+    gn = (gt_depth - t_gt) / s_gt
+    arr = (dn - gn) ** 2
+    arr = torch.where(arr > torch.quantile(arr, 0.8, dim=1)[..., None], torch.zeros_like(arr), arr)
+    return arr.mean() * lambda_depth
+
+
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def alg_bytes(P, Pn, V, R, N, T):
+    """Algorithmic bytes per stage. preprocess_bwd is the dense pass alone; the zero fill of the dense gradient rows
+    is its own stage (executed by memsets on a side stream)."""
+    return {
+        "preprocess_fwd": 20 * P + 52 * Pn + 239 * V,
+        "binning": 8 * P + (8 * P + 12 * V + 12 * R) + 24 * R + (8 * R + 8 * T),
+        "render_fwd": 28 * R + 24 * V + 32 * N,
+        "render_bwd": 52 * R + 36 * N + 48 * V,
+        "preprocess_bwd": (56 + 36) * V + (303 + 232) * V,
+        "grad_fills": 312 * (P - V),
+    }
+
+
+class Timer:
+    """K timed steps bracketed by barrier + synchronize, CUDA events on the current stream, max over ranks."""
+
+    def __init__(self, device, dist, extra_warmup):
+        self.device, self.dist, self.extra_warmup, self.stats, self.windows = device, dist, extra_warmup, {}, []
+
+    def run(self, fn, steps, warmup, name=None):
+        import gc
+
+        for _ in range(warmup + self.extra_warmup):
+            fn()
+        # a generation-2 Python GC pass walks every object torch/numpy created at import time (30-40 ms, seen as one slow step):
+        # collect now and freeze the survivors so no such pass can land inside the timed region
+        gc.collect()
+        gc.freeze()
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ms0 = torch.cuda.memory_stats(self.device)
+        host_t = []
+        t0 = time.time()
+        evs[0].record()
+        for i in range(steps):
+            h0 = time.perf_counter()
+            fn()
+            host_t.append((time.perf_counter() - h0) * 1e3)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        ms1 = torch.cuda.memory_stats(self.device)
+        ms = evs[0].elapsed_time(evs[steps])  # the K steps, bracketed
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        self.stats[name or fn.__name__] = {
+            "median_ms": round(per[len(per) // 2], 4), "min_ms": round(per[0], 4), "max_ms": round(per[-1], 4),
+            "host_max_ms": round(max(host_t), 3), "host_median_ms": round(sorted(host_t)[len(host_t) // 2], 3),
+            "cudaMalloc_calls": int(ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0)),
+            "cudaFree_calls": int(ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0))}
+        if self.dist is not None:
+            t = torch.tensor([ms], device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+            self.dist.barrier()
+        self.windows.append((t0, t1))
+        return ms
+
+
+def event_time(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def stage_views(cams, gt_img, gt_dep, device, copy_stream):
+    """Double-buffered H2D of a view's inputs (camera + ground truth) from pinned memory on a copy stream, like a prefetching data
+    loader; the compute stream waits on the event before using them. Returns next_view(v) -> (mats, gt image, gt depth)."""
+    pending = {}
+    V = len(cams)
+
+    def stage(v):
+        with torch.cuda.stream(copy_stream):
+            cam = cams[v]
+            mats = [cam[k + "_pin"].to(device, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos")]
+            gi = gt_img[v].to(device, non_blocking=True) if gt_img is not None else None
+            gd = gt_dep[v].to(device, non_blocking=True) if gt_dep is not None else None
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return mats, gi, gd, ev
+
+    def next_view(v):
+        if v not in pending:
+            pending[v] = stage(v)
+        mats, gi, gd, ev = pending.pop(v)
+        torch.cuda.current_stream().wait_event(ev)
+        for t in mats + [gi, gd]:
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream())
+        nv = (v + 1) % V
+        pending[nv] = stage(nv)  # the next view's (next step's) inputs travel while this view computes
+        return mats, gi, gd
+
+    return next_view
+
+
+def make_host_dataset(V, W, Hh, seed, with_depth=True):
+    g = torch.Generator().manual_seed(seed)
+    gt_img = [torch.rand(3, Hh, W, generator=g).pin_memory() for _ in range(V)]
+    gt_dep = [torch.rand(1, Hh, W, generator=g).pin_memory() for _ in range(V)] if with_depth else None
+    return gt_img, gt_dep
+
+
+def pin_cameras(cams, device):
+    for cam in cams:
+        for k in ["viewmatrix", "projmatrix", "campos"]:
+            cam[k + "_pin"] = cam[k].clone().pin_memory()
+            cam[k + "_dev"] = cam[k].to(device)
+
+
+def train_loss(color, depth, gi, gd, depth_loss_fn):
+    """The reference's training loss shape with depth supervision (train.py:107-121, using_depth / localrf): L1 on the colour
+    (the SSIM term is the separate `gsr_image_loss` row) + compute_depth_loss(1 / (depth / (max + 1e-5)).clamp(1e-6),
+    gt_depth, 0.1)."""
+    dn = depth / (depth.max() + 1e-5)  # gaussian_renderer/__init__.py:375
+    return (color - gi).abs().mean() + depth_loss_fn(1 / dn.clamp(1e-6), gd, 0.1)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
 class RefRasterize(torch.autograd.Function):
     """The reference's _RasterizeGaussians (diff_gaussian_rasterization/__init__.py:46-166) restated over the reference's
     OWN compiled extension (oracle/_ref/ref_dgr_C.so): same positional argument order, same saved tensors, same outputs."""
@@ -126,155 +363,210 @@ class RefRasterize(torch.autograd.Function):
         return None, g_m3d, g_m2d, g_sh, None, g_seg, g_op, g_sc, g_rot, None, None
 
 
-def make_rasterize_fn(impl, pkg):
-    """Returns f(leaves, means2D, rs) -> (color, radii, depth, alpha, segment) for the chosen implementation."""
-    if impl == "ours":
-        def f(lv, means2D, rs):
-            return pkg.GaussianRasterizer(rs)(means3D=lv["means3D"], means2D=means2D, opacities=lv["opacities"], shs=lv["shs"],
-                                              segments=lv["segments"], scales=lv["scales"], rotations=lv["rotations"])
-        return f
-    import helpers as H
-
-    C = H.ref_dgr()
-    if C is None:
+def load_ref_ext():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    try:
+        return importlib.import_module("ref_dgr_C")
+    except Exception as e:
+        print("bench: reference CUDA build unavailable:", e, file=sys.stderr, flush=True)
         return None
-    e = torch.empty(0)
-
-    def f(lv, means2D, rs):
-        return RefRasterize.apply(C, lv["means3D"], means2D, lv["shs"], e, lv["segments"], lv["opacities"], lv["scales"], lv["rotations"], e, rs)
-    return f
 
 
-# ------------------------------------------------------------------------------------------------ workload
-LEAVES = ["means3D", "shs", "segments", "opacities", "scales", "rotations"]  # 3+48+2+1+3+4 = 61 floats per Gaussian
-
-
-def build_workload(pkg, syn, name, device, views, view_base, seed_override=None):
-    P, W, Hh, seed = syn.CONFIGS[name]
-    gs, _ = syn.make_scene(name)
-    cams = [syn.make_camera(W, Hh, yaw_deg=45.0 * (view_base + v)) for v in range(views)]
-    ug = syn.upstream_grads(W, Hh, seed, with_depth=True)
-    return dict(P=P, W=W, H=Hh, seed=seed, gs={k: v.to(device) for k, v in gs.items()}, cams=cams,
-                ug={k: (v.to(device) if v is not None else None) for k, v in ug.items()})
-
-
-def settings_for(pkg, cam, bg, device):
-    return pkg.GaussianRasterizationSettings(
-        image_height=cam["H"], image_width=cam["W"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg, scale_modifier=1.0,
-        viewmatrix=cam["viewmatrix_dev"], projmatrix=cam["projmatrix_dev"], sh_degree=3, campos=cam["campos_dev"], prefiltered=False, debug=False)
-
-
-def _claim_stdout():
-    """NCCL / torchrun print banners to fd 1; the contract is ONE JSON line on stdout. Park the real stdout on a private fd
-    and point fd 1 at stderr for the rest of the run."""
-    sys.stdout.flush()
-    real = os.dup(1)
-    os.dup2(2, 1)
-    return os.fdopen(real, "w")
-
-
-def main():
-    out = _claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
-    ap.add_argument("--views-per-rank", type=int, default=1)
-    ap.add_argument("--grad-exchange", default="peer", choices=["peer", "packets", "dense"],
-                    help="N>1: peer = gather kernel pulls every rank's 68-B gradient packets over NVLink peer memory (default); "
-                         "packets = NCCL all-gather of the packets, then the gather kernel; dense = all-reduce of the flat buffer")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-stage-profile", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    # the first ~8 steps grow the caching allocator's pools (cudaMalloc of the GB-sized state/gradient buffers): always run
-    # at least that many untimed steps before the W warm-ups the caller asked for are considered done
-    args.extra_warmup = max(0, 8 - args.warmup) if os.environ.get("GSR_BENCH_MIN_WARMUP", "1") == "1" else 0
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+def reference_arm(args, out):
+    """`--impl reference`: the reference's CUDA rasterizer through its own pybind entry points. Nothing of the product is imported."""
+    syn = load_synthetic()
     have_gpu = torch.cuda.is_available()
-
-    if args.impl == "reference" and world > 1 and rank != 0:
-        return 0  # the reference is single-GPU: rank 0 alone runs and prints it
-
-    syn = importlib.import_module(PKG + ".synthetic")
-    if args.impl == "reference" and (not have_gpu or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dgr_C.so"))):
+    C = load_ref_ext() if have_gpu else None
+    if C is None:
         return reference_cpu_port(args, syn, out)
-
-    if not have_gpu:
-        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
-    # clocks are sampled for the whole run; starting nvidia-smi here keeps its (slow, driver-locking) start-up out of the
-    # timed regions
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     sampler = ClockSampler(local_rank)
-    if rank == 0 and not os.environ.get("GSR_BENCH_NO_SAMPLER"):
+    if not os.environ.get("GSR_BENCH_NO_SAMPLER"):
         sampler.start()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    pkg = load_ours()  # also provides GaussianRasterizationSettings for the reference arm
-    dist = None
-    if world > 1 and args.impl == "ours":
-        import torch.distributed as dist_
-
-        dist = dist_
-        dist.init_process_group("nccl", device_id=device)
-    nranks = world if args.impl == "ours" else 1
-
-    rasterize = make_rasterize_fn(args.impl, pkg)
-    if rasterize is None:
-        return reference_cpu_port(args, syn, out)
-
-    V = args.views_per_rank
-    wl = build_workload(pkg, syn, args.workload, device, V, rank * V)
-    P, W, Hh = wl["P"], wl["W"], wl["H"]
-    N = W * Hh
+    name = args.workload
+    fwd_only = name == "cfg5"
+    V = args.views_per_rank or 1
+    P, W, Hh, seed = syn.CONFIGS[name]
+    gs, _ = syn.make_scene(name)  # cfg5: the four sub-scenes concatenated once, as visualizer._merge_scenes does at load time
+    cams = [syn.make_camera(W, Hh, yaw_deg=45.0 * v) for v in range(V)]
+    pin_cameras(cams, device)
+    ug = {k: (v.to(device) if v is not None else None) for k, v in syn.upstream_grads(W, Hh, seed, with_depth=True).items()}
+    leaves = {k: gs[k].to(device).requires_grad_(not fwd_only) for k in LEAVES}
     bg = torch.zeros(3, device=device)
-    for cam in wl["cams"]:
-        for k in ["viewmatrix", "projmatrix", "campos"]:
-            cam[k + "_pin"] = cam[k].clone().pin_memory()
-            cam[k + "_dev"] = cam[k].to(device)
-    leaves = {k: wl["gs"][k].clone().requires_grad_(True) for k in LEAVES}
-    ug = wl["ug"]
+    e = torch.empty(0)
+    N = W * Hh
 
-    # host-side "dataset" for the e2e leg: ground-truth image and (inverse, normalised) depth per view, pinned
-    g = torch.Generator().manual_seed(77 + rank)
-    gt_img = [torch.rand(3, Hh, W, generator=g).pin_memory() for _ in range(V)]
-    gt_dep = [torch.rand(1, Hh, W, generator=g).pin_memory() for _ in range(V)]
-    h2d_bytes = V * (gt_img[0].numel() + gt_dep[0].numel() + 16 + 16 + 3) * 4
-    d2h_bytes = V * 4
+    def rasterize(rs, means2D):
+        return RefRasterize.apply(C, leaves["means3D"], means2D, leaves["shs"], e, leaves["segments"], leaves["opacities"], leaves["scales"],
+                                  leaves["rotations"], e, rs)
 
     def zero_grads():
         for v in leaves.values():
             v.grad = None
 
-    e2e_sets = []
-    xstate = {}  # sticky blob capacity of the packet exchange
+    def step_device():
+        zero_grads()
+        for v in range(V):
+            rs = make_settings(RefSettings, cams[v], bg)
+            if fwd_only:
+                with torch.no_grad():
+                    rasterize(rs, torch.zeros_like(leaves["means3D"]))
+                continue
+            means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+            color, radii, depth, alpha, segment = rasterize(rs, means2D)
+            torch.autograd.backward([color, depth], [ug["color"], ug["depth"]])
 
-    def allreduce_grads():
-        if dist is None:
-            return
-        if use_peer:
-            px.exchange(flat, leaves, all_campos, 3)
-            return
-        if use_packets and e2e_sets:
-            mv.exchange_packets(Dmod, dist, flat, leaves, e2e_sets, all_campos, 3, nranks, state=xstate)
-            e2e_sets.clear()
-            return
-        if flat is not None:
-            flat.allreduce(dist)
-            return
-        for k in LEAVES:
-            dist.all_reduce(leaves[k].grad)
+    gt_img, gt_dep = make_host_dataset(V, W, Hh, 77, with_depth=not fwd_only)
+    h2d_bytes = V * ((gt_img[0].numel() + gt_dep[0].numel()) * 4 if not fwd_only else 0) + V * (16 + 16 + 3) * 4
+    d2h_bytes = V * (3 * N * 4 if fwd_only else 4)
+    next_view = stage_views(cams, None if fwd_only else gt_img, gt_dep, device, torch.cuda.Stream(device=device))
+    host_img = torch.empty(3, Hh, W).pin_memory() if fwd_only else None
+    loss_host = [0.0]
 
+    def step_e2e():
+        zero_grads()
+        total = None
+        for v in range(V):
+            mats, gi, gd = next_view(v)
+            rs = make_settings(RefSettings, cams[v], bg, mats)
+            if fwd_only:  # viewer frame: camera in, image out
+                with torch.no_grad():
+                    color = rasterize(rs, torch.zeros_like(leaves["means3D"]))[0]
+                host_img.copy_(color, non_blocking=True)
+                continue
+            means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+            color, radii, depth, alpha, segment = rasterize(rs, means2D)
+            loss = train_loss(color, depth, gi, gd, reference_depth_loss)
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if fwd_only:
+            torch.cuda.current_stream().synchronize()
+        else:
+            loss_host[0] = float(total.item())  # D2H read of the step's result
+
+    timer = Timer(device, None, max(0, 8 - args.warmup))
+    ms_dev = timer.run(step_device, args.steps, args.warmup)
+    ms_e2e = timer.run(step_e2e, args.steps, args.warmup)
+    clocks = sampler.summary(timer.windows)
+    sampler.stop()
+
+    def fwd_only_fn():
+        with torch.no_grad():
+            return rasterize(make_settings(RefSettings, cams[0], bg), torch.zeros_like(leaves["means3D"]))
+
+    fwd_ms = event_time(fwd_only_fn, max(10, min(50, args.steps)))
+
+    # realised statistics from the reference's own buffers
+    import helpers as H  # tests/helpers.py: parse_ref_state only needs torch (the product package is imported lazily by other helpers)
+
+    with torch.no_grad():
+        rs = make_settings(RefSettings, cams[0], bg)
+        R, color, depth, segment, alpha, radii, geom, binb, img = C.rasterize_gaussians(
+            bg, leaves["means3D"], e, leaves["segments"], leaves["opacities"], leaves["scales"], leaves["rotations"], 1.0, e, rs.viewmatrix,
+            rs.projmatrix, rs.tanfovx, rs.tanfovy, Hh, W, leaves["shs"], 3, rs.campos, False, False)
+        Vn = int((radii > 0).sum())
+        Pn = int(C.mark_visible(leaves["means3D"], rs.viewmatrix, rs.projmatrix).sum())
+        st = H.parse_ref_state(P, W, Hh, int(R), geom, binb, img)
+        E_b = int(st["n_contrib"].to(torch.int64).sum())
+    T = ((W + 15) // 16) * ((Hh + 15) // 16)
+    stats = dict(P=P, Pn=Pn, V=Vn, R=int(R), N=N, T=T, E_b=E_b)
+    B = alg_bytes(P, Pn, Vn, int(R), N, T)
+    if fwd_only:
+        bytes_step = B["preprocess_fwd"] + B["binning"] + B["render_fwd"]
+    else:
+        bytes_step = sum(B.values())
+    peak, peak_src = hbm_peak()
+    views_total = V * args.steps
+    value = views_total / (ms_dev / 1e3)
+    e2e_value = views_total / (ms_e2e / 1e3)
+    ach = bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9
+    line = {
+        "metric": METRICS[name], "value": round(value, 4), "unit": "frames/s" if fwd_only else "it/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": "%s: %d Gaussians SH3, %dx%d, reference CUDA rasterizer (oracle/_ref/ref_dgr_C.so) %s, %d view(s)/step"
+                               % (name, P, W, Hh, "forward only" if fwd_only else "fwd (colour+depth+alpha+segment) + bwd (dL/dcolour, dL/ddepth)", V),
+                   "views_per_rank": V, "l2": "inputs (%.2f GB of parameters) are larger than the 126 MB L2" % (61 * 4 * P / 1e9), "stats": stats,
+                   "alg_bytes_per_step": bytes_step},
+        "e2e": {"value": round(e2e_value, 4), "unit": "frames/s" if fwd_only else "it/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": round(ms_e2e / args.steps, 4), "loss": loss_host[0],
+                "loss_fn": "L1 colour + compute_depth_loss (median / quantile, utils/loss_utils.py:88-102) in torch"},
+        "gpu_launches": 0, "clocks": clocks,
+        "roofline": {"kernel": "whole step (reference CUDA)", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src},
+        "cpu_baseline": {"value": round(value, 4), "unit": "frames/s" if fwd_only else "it/s", "cores": 0, "kind": "reference",
+                         "sample": "full %s on the GPU: the reference's own implementation of this path is CUDA (oracle/_ref/ref_dgr_C.so); "
+                                   "it ships no CPU path" % name},
+        "step_ms": timer.stats, "fwd_ms_per_frame": round(fwd_ms, 4),
+    }
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def ours_arm(args, out):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    # clocks are sampled for the whole run; starting the sampler here keeps its start-up out of the timed regions
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get("GSR_BENCH_NO_SAMPLER"):
+        sampler.start()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    pkg = importlib.import_module(PKG)
+    syn = importlib.import_module(PKG + ".synthetic")
     mv = importlib.import_module(PKG + ".multiview")
-    use_flat = args.impl == "ours" and (nranks > 1 or V > 1)
-    flat = mv.FlatGradients(P, device) if use_flat else None
+    losses = importlib.import_module(PKG + ".losses")
     Dmod = pkg.diff_gaussian_rasterization
+    L = pkg._lib.lib()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=device)
+    nranks = world
+
+    # ---- workload: which config, how many views per rank ----
+    name = args.workload or ("cfg4" if nranks > 1 else "cfg3")
+    fwd_only = name == "cfg5"
+    if args.views_per_rank:
+        V, scaling, B_step = args.views_per_rank, "weak", args.views_per_rank * nranks
+    else:
+        B_step = args.views_per_step or (8 if (name == "cfg4" and nranks > 1) else nranks)
+        if B_step % nranks:
+            raise SystemExit("--views-per-step %d is not a multiple of %d ranks" % (B_step, nranks))
+        V = B_step // nranks
+        scaling = "strong" if (nranks > 1 and (args.views_per_step or name == "cfg4")) else "weak"
+    if fwd_only and nranks > 1:
+        raise SystemExit("cfg5 is a single-view render: it does not shard (replicas only); run it with --gpus 1")
+    P, W, Hh, seed = syn.CONFIGS[name]
+    N = W * Hh
+    cams = [syn.make_camera(W, Hh, yaw_deg=45.0 * (rank * V + v)) for v in range(V)]
+    pin_cameras(cams, device)
+    bg = torch.zeros(3, device=device)
+    ug = {k: (v.to(device) if v is not None else None) for k, v in syn.upstream_grads(W, Hh, seed, with_depth=True).items()}
+    parts = None
+    if fwd_only:  # four resident sub-scenes, rendered without concatenation
+        parts = [{k: v.to(device) for k, v in syn.make_gaussians(P // 4, seed + i, scale_P=P).items()} for i in range(4)]
+        leaves = None
+    else:
+        gs, _ = syn.make_scene(name)
+        leaves = {k: gs[k].to(device).requires_grad_(True) for k in LEAVES}
+        del gs
+    GS = pkg.GaussianRasterizationSettings
     empty = torch.empty(0)
 
+    use_flat = (not fwd_only) and (nranks > 1 or V > 1)
+    flat = mv.FlatGradients(P, device) if use_flat else None
     use_packets = use_flat and dist is not None and args.grad_exchange == "packets"
     use_peer = use_flat and dist is not None and args.grad_exchange == "peer"
     px = None
@@ -288,291 +580,264 @@ def main():
     all_campos = None
     if use_packets or use_peer:  # every rank knows every camera of the step
         all_campos = [[syn.make_camera(W, Hh, yaw_deg=45.0 * (r * V + v))["campos"].to(device) for v in range(V)] for r in range(nranks)]
+    xstate = {}  # sticky blob capacity of the NCCL packet exchange
 
-    def step_device_flat():
-        """multi-view / multi-GPU step. dense: every view's backward adds into ONE flat gradient buffer, one NCCL all-reduce.
-        packets: every view's backward emits 68-B packets of its visible Gaussians + an id map, NCCL all-gathers, then one
-        gather pass that sums all views and writes every dense row once."""
-        sets = []
-        for v in range(V):
-            rs = settings_for(pkg, wl["cams"][v], bg, device)
-            with torch.no_grad():
-                fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"], leaves["scales"],
-                                           leaves["rotations"], empty, rs)
-                if use_peer:
-                    px.view_backward(leaves, rs, fwd, ug, v)
-                elif use_packets:
-                    sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug, capacity=xstate.get("cap", 0)))
-                else:
-                    mv.native_view_backward(Dmod, leaves, rs, fwd, ug, flat, first=(v == 0))
-        if use_peer:
+    def zero_grads():
+        for v in leaves.values():
+            v.grad = None
+
+    def rasterize(rs, means2D):
+        return pkg.GaussianRasterizer(rs)(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves["shs"],
+                                          segments=leaves["segments"], scales=leaves["scales"], rotations=leaves["rotations"])
+
+    def render_parts(rs):
+        return pkg.GaussianRasterizer(rs).forward_parts(parts)
+
+    def native_forward(rs):
+        return Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"], leaves["scales"],
+                                    leaves["rotations"], empty, rs)
+
+    def flat_backward(rs, fwd, pg, v, mode, sets):
+        if mode == "peer":
+            px.view_backward(leaves, rs, fwd, pg, v)
+        elif mode == "packets":
+            sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, pg, capacity=xstate.get("cap", 0)))
+        else:
+            mv.native_view_backward(Dmod, leaves, rs, fwd, pg, flat, first=(v == 0))
+
+    def flat_exchange(mode, sets):
+        if dist is None:
+            return
+        if mode == "peer":
             px.exchange(flat, leaves, all_campos, 3)
-        elif use_packets:
+        elif mode == "packets":
             mv.exchange_packets(Dmod, dist, flat, leaves, sets, all_campos, 3, nranks, state=xstate)
-        elif dist is not None:
+        else:
             flat.allreduce(dist)
 
+    mode = "peer" if use_peer else ("packets" if use_packets else "dense")
+
+    def step_flat(mode_=None):
+        """multi-view / multi-GPU step: every view's backward goes into ONE flat gradient buffer (dense: added in place, then one
+        NCCL all-reduce; packets / peer: compact packets, then one gather pass that writes every dense row once)."""
+        m = mode_ or mode
+        sets = []
+        for v in range(V):
+            rs = make_settings(GS, cams[v], bg)
+            with torch.no_grad():
+                fwd = native_forward(rs)
+                flat_backward(rs, fwd, ug, v, m, sets)
+        flat_exchange(m, sets)
+
     def step_device():
+        if fwd_only:
+            with torch.no_grad():
+                render_parts(make_settings(GS, cams[0], bg))
+            return
         if use_flat:
-            return step_device_flat()
+            return step_flat()
         zero_grads()
         for v in range(V):
-            rs = settings_for(pkg, wl["cams"][v], bg, device)
+            rs = make_settings(GS, cams[v], bg)
             means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-            color, radii, depth, alpha, segment = rasterize(leaves, means2D, rs)
+            color, radii, depth, alpha, segment = rasterize(rs, means2D)
             torch.autograd.backward([color, depth], [ug["color"], ug["depth"]])
-        allreduce_grads()
 
+    # ---- e2e: host buffers in, loss out ----
+    gt_img, gt_dep = make_host_dataset(V, W, Hh, 77 + rank, with_depth=not fwd_only)
+    h2d_bytes = V * ((gt_img[0].numel() + gt_dep[0].numel()) * 4 if not fwd_only else 0) + V * (16 + 16 + 3) * 4
+    d2h_bytes = V * (3 * N * 4 if fwd_only else 4)
+    next_view = stage_views(cams, None if fwd_only else gt_img, gt_dep, device, torch.cuda.Stream(device=device))
+    host_img = torch.empty(3, Hh, W).pin_memory() if fwd_only else None
     loss_host = [0.0]
-    copy_stream = torch.cuda.Stream(device=device)
-
-    def stage_view(v):
-        """H2D of view v's inputs (camera + ground truth) from pinned memory on the copy stream, double-buffered like a
-        prefetching data loader; the compute stream waits on the event before using them."""
-        with torch.cuda.stream(copy_stream):
-            cam = wl["cams"][v]
-            mats = [cam[k + "_pin"].to(device, non_blocking=True) for k in ("viewmatrix", "projmatrix", "campos")]
-            gi = gt_img[v].to(device, non_blocking=True)
-            gd = gt_dep[v].to(device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return mats, gi, gd, ev
-
-    pending = {}
+    depth_loss_fn = getattr(losses, "depth_loss", None) or reference_depth_loss
+    depth_loss_name = ("gsr_depth_loss (native median / quantile radix select)" if depth_loss_fn is not reference_depth_loss
+                       else "compute_depth_loss in torch")
 
     def step_e2e():
-        zero_grads()
+        if fwd_only:
+            mats, _, _ = next_view(0)
+            with torch.no_grad():
+                color = render_parts(make_settings(GS, cams[0], bg, mats))[0]
+            host_img.copy_(color, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return
+        if not use_flat:
+            zero_grads()
         total = None
+        sets = []
         for v in range(V):
-            cam = wl["cams"][v]
-            if v not in pending:
-                pending[v] = stage_view(v)
-            mats, gi, gd, ev = pending.pop(v)
-            torch.cuda.current_stream().wait_event(ev)
-            for t in mats + [gi, gd]:
-                t.record_stream(torch.cuda.current_stream())
-            nv = (v + 1) % V
-            pending[nv] = stage_view(nv)  # next view's (next step's) inputs travel while this view computes
-            rs = settings_for(pkg, dict(cam, viewmatrix_dev=mats[0], projmatrix_dev=mats[1], campos_dev=mats[2]), bg, device)
+            mats, gi, gd = next_view(v)
+            rs = make_settings(GS, cams[v], bg, mats)
             if use_flat:
                 with torch.no_grad():
-                    fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"],
-                                               leaves["scales"], leaves["rotations"], empty, rs)
+                    fwd = native_forward(rs)
                 color, depth = fwd[1].requires_grad_(True), fwd[2].requires_grad_(True)
-                dn = depth / (depth.max() + 1e-5)
-                loss = (color - gi).abs().mean() + 0.1 * (dn - gd).abs().mean()
-                loss.backward()  # pixel gradients only; the rasterizer backward runs natively into the flat buffer
+                loss = train_loss(color, depth, gi, gd, depth_loss_fn)
+                loss.backward()  # pixel gradients only; the rasterizer backward runs natively into the flat buffer / as packets
                 with torch.no_grad():
-                    pg = {"color": color.grad, "depth": depth.grad}
-                    if use_peer:
-                        px.view_backward(leaves, rs, fwd, pg, v)
-                    elif use_packets:
-                        e2e_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, pg, capacity=xstate.get("cap", 0)))
-                    else:
-                        mv.native_view_backward(Dmod, leaves, rs, fwd, pg, flat, first=(v == 0))
+                    flat_backward(rs, fwd, {"color": color.grad, "depth": depth.grad}, v, mode, sets)
             else:
                 means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-                color, radii, depth, alpha, segment = rasterize(leaves, means2D, rs)
-                dn = depth / (depth.max() + 1e-5)  # gaussian_renderer/__init__.py:375
-                loss = (color - gi).abs().mean() + 0.1 * (dn - gd).abs().mean()  # train.py:111-121 shape (L1 + depth term)
+                color, radii, depth, alpha, segment = rasterize(rs, means2D)
+                loss = train_loss(color, depth, gi, gd, depth_loss_fn)
                 loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        allreduce_grads()
+        if use_flat:
+            flat_exchange(mode, sets)
         loss_host[0] = float(total.item())  # D2H read of the step's result
 
-    step_stats = {}
+    # ---- N > 1: correctness of the exchange, before anything is timed ----
+    exchange_parity = None
+    if dist is not None and use_flat:
+        step_flat("dense")
+        ref_buf = flat.buffer.clone()
+        step_flat()
+        got = flat.buffer
+        rel = float((got - ref_buf).abs().max() / ref_buf.abs().max().clamp_min(1e-30))
+        hi, lo = got.clone(), got.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(hi, lo))
+        nz = int((ref_buf != 0).sum())
+        exchange_parity = {"mode": mode, "vs": "dense in-place accumulation + one ncclAllReduce of the flat buffer", "max_rel_err": rel,
+                           "cross_rank_bit_identical": same, "nonzero_grad_floats": nz, "views": V * nranks}
+        del ref_buf, hi, lo
 
-    def timed(fn, steps, warmup):
-        import gc
-
-        for _ in range(warmup + args.extra_warmup):
-            fn()
-        # a full (generation-2) Python GC pass walks every object torch/numpy created at import time (30-40 ms, seen as a
-        # single slow step); collect now and freeze the survivors so no such pass can land inside the timed region
-        gc.collect()
-        gc.freeze()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        ms0 = torch.cuda.memory_stats(device)
-        host_t = []
-        t0 = time.time()
-        evs[0].record()
-        for i in range(steps):
-            h0 = time.perf_counter()
-            fn()
-            host_t.append((time.perf_counter() - h0) * 1e3)
-            evs[i + 1].record()
-        torch.cuda.synchronize()
-        t1 = time.time()
-        ms1 = torch.cuda.memory_stats(device)
-        ms = evs[0].elapsed_time(evs[steps])  # the K steps, bracketed
-        if os.environ.get("GSR_BENCH_DEBUG_STEPS"):
-            print("STEPS", fn.__name__, [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(steps)], file=sys.stderr, flush=True)
-        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
-        step_stats[fn.__name__] = {"median_ms": round(per[len(per) // 2], 4), "min_ms": round(per[0], 4), "max_ms": round(per[-1], 4),
-                                   "host_max_ms": round(max(host_t), 3), "host_median_ms": round(sorted(host_t)[len(host_t) // 2], 3),
-                                   "cudaMalloc_calls": int(ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0)),
-                                   "cudaFree_calls": int(ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0))}
-        if dist is not None:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            dist.barrier()
-        return ms, t0, t1
-
-    if os.environ.get("GSR_BENCH_DEBUG") and args.impl == "ours":
-        Ld = pkg._lib.lib()
-        Ld.gsr_set_profiling(1)
-        for name, fn in [("device", step_device), ("e2e", step_e2e), ("device", step_device), ("e2e", step_e2e)]:
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            t0 = time.time()
-            fn()
-            torch.cuda.synchronize()
-            print("DEBUG", name, "wall_ms=%.3f" % ((time.time() - t0) * 1e3), pkg._lib.stage_times(), file=sys.stderr, flush=True)
-        Ld.gsr_set_profiling(0)
-
-    L = pkg._lib.lib()
+    timer = Timer(device, dist, max(0, 8 - args.warmup) if os.environ.get("GSR_BENCH_MIN_WARMUP", "1") == "1" else 0)
     launches0 = int(L.gsr_launch_count())
-    ms_dev, t0, t1 = timed(step_device, args.steps, args.warmup)
-    launches_timed = (int(L.gsr_launch_count()) - launches0) * args.steps // (args.steps + args.warmup + args.extra_warmup)
-    clocks = sampler.summary(t0, t1) if rank == 0 else None
-    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_dev = timer.run(step_device, args.steps, args.warmup)
+    launches_timed = (int(L.gsr_launch_count()) - launches0) * args.steps // (args.steps + args.warmup + timer.extra_warmup)
+    ms_e2e = timer.run(step_e2e, args.steps, args.warmup)
+    clocks = sampler.summary(timer.windows) if rank == 0 else None
     if rank == 0:
         sampler.stop()
 
     comm_ms = None
-    if dist is not None:
-        def comm_only():
-            if use_peer:
-                px.exchange(flat, leaves, all_campos, 3)
-            elif use_packets:
-                mv.exchange_packets(Dmod, dist, flat, leaves, comm_sets, all_campos, 3, nranks, state=xstate)
-            else:
-                flat.allreduce(dist)
+    if dist is not None and use_flat:
         comm_sets = []
-        if use_packets:
+        if mode == "packets":
             with torch.no_grad():
                 for v in range(V):
-                    rs = settings_for(pkg, wl["cams"][v], bg, device)
-                    fwd = Dmod._forward_native(leaves["means3D"], leaves["shs"], empty, leaves["segments"], leaves["opacities"],
-                                               leaves["scales"], leaves["rotations"], empty, rs)
-                    comm_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, fwd, ug, capacity=xstate.get("cap", 0)))
-        for _ in range(2):
-            comm_only()
-        torch.cuda.synchronize()
+                    rs = make_settings(GS, cams[v], bg)
+                    comm_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, native_forward(rs), ug, capacity=xstate.get("cap", 0)))
         dist.barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(5):
-            comm_only()
-        c1.record()
-        torch.cuda.synchronize()
-        comm_ms = c0.elapsed_time(c1) / 5
+        comm_ms = event_time(lambda: flat_exchange(mode, comm_sets), 5, warm=2)
 
-    # forward-only ms/frame (the second half of BASELINE.json's metric), same workload, rank-local
-    def fwd_only():
+    def fwd_only_fn():
         with torch.no_grad():
-            rs = settings_for(pkg, wl["cams"][0], bg, device)
-            means2D = torch.zeros_like(leaves["means3D"])
-            return rasterize(leaves, means2D, rs)
+            rs = make_settings(GS, cams[0], bg)
+            return render_parts(rs) if fwd_only else rasterize(rs, torch.zeros_like(leaves["means3D"]))
 
-    for _ in range(5):
-        fwd_only()
-    torch.cuda.synchronize()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    nf = max(10, min(50, args.steps))
-    for _ in range(nf):
-        fwd_only()
-    f1.record()
-    torch.cuda.synchronize()
-    fwd_ms = f0.elapsed_time(f1) / nf
+    fwd_ms = event_time(fwd_only_fn, max(10, min(50, args.steps)), warm=5)
+
+    # the 8-views-per-step batch of BASELINE config 4 on ONE GPU: the strong-scaling base of the N > 1 lines
+    cfg4_1gpu = None
+    if nranks == 1 and name == "cfg3" and not args.views_per_rank and not args.views_per_step and not args.no_cfg4_base:
+        cams8 = [syn.make_camera(W, Hh, yaw_deg=45.0 * v) for v in range(8)]
+        pin_cameras(cams8, device)
+        flat8 = mv.FlatGradients(P, device)
+
+        def step8():
+            for v in range(8):
+                rs = make_settings(GS, cams8[v], bg)
+                with torch.no_grad():
+                    mv.native_view_backward(Dmod, leaves, rs, native_forward(rs), ug, flat8, first=(v == 0))
+
+        ms8 = event_time(step8, max(3, min(10, args.steps // 2)), warm=2)
+        cfg4_1gpu = {"views_per_step": 8, "ms_per_step": round(ms8, 4), "value": round(8 / (ms8 * 1e-3), 3), "unit": "it/s (views/s)",
+                     "path": "8 views accumulated into one flat gradient buffer (gsr_backward accumulate), no exchange"}
+        del flat8
 
     views_total = V * nranks * args.steps
     value = views_total / (ms_dev / 1e3)
     e2e_value = views_total / (ms_e2e / 1e3)
 
-    # ---- realised workload statistics (one forward, untimed) ----
+    # ---- realised workload statistics + algorithmic work (one forward, untimed) ----
     with torch.no_grad():
-        rs = settings_for(pkg, wl["cams"][0], bg, device)
-        D = pkg.diff_gaussian_rasterization
-        e = torch.empty(0)
-        R, color, depth, segment, alpha, radii, geom, binb, img = D._forward_native(leaves["means3D"], leaves["shs"], e, leaves["segments"],
-                                                                                   leaves["opacities"], leaves["scales"], leaves["rotations"], e, rs)
+        rs = make_settings(GS, cams[0], bg)
+        if fwd_only:
+            catd = {k: torch.cat([p[k] for p in parts], 0) for k in ("means3D",)}
+            R, color, depth, segment, alpha, radii, geom, binb, img = Dmod._forward_parts_native(parts, rs)
+            means_all = catd["means3D"]
+        else:
+            R, color, depth, segment, alpha, radii, geom, binb, img = native_forward(rs)
+            means_all = leaves["means3D"]
         Vn = int((radii > 0).sum())
-        Pn = int(pkg.mark_visible(leaves["means3D"], rs.viewmatrix, rs.projmatrix).sum())
+        Pn = int(pkg.mark_visible(means_all, rs.viewmatrix, rs.projmatrix).sum())
         T = ((W + 15) // 16) * ((Hh + 15) // 16)
+        work = Dmod.count_work(P, W, Hh, geom, binb, img, R)
         del color, depth, segment, alpha, geom, binb, img
-    stats = dict(P=P, Pn=Pn, V=Vn, R=int(R), N=N, T=T)
-    # algorithmic bytes (SURVEY.md 8d)
-    B = {
-        "preprocess_fwd": 20 * P + 52 * Pn + 239 * Vn,
-        "binning": 8 * P + (8 * P + 12 * Vn + 12 * R) + 24 * R + (8 * R + 8 * T),
-        "render_fwd": 28 * R + 24 * Vn + 32 * N,
-        "render_bwd": 52 * R + 36 * N + 48 * Vn,
-        "preprocess_bwd": (56 + 36) * Vn + (303 + 232) * Vn + 312 * (P - Vn),
-    }
-    bytes_step = sum(B.values())
+    stats = dict(P=P, Pn=Pn, V=Vn, R=int(R), N=N, T=T, **work)
+    B = alg_bytes(P, Pn, Vn, int(R), N, T)
+    bytes_step = (B["preprocess_fwd"] + B["binning"] + B["render_fwd"]) if fwd_only else sum(B.values())
+    peak, peak_src = hbm_peak()
+    # compositing work model (SURVEY.md 8d item 2)
+    flops = {"render_fwd": 21 * work["E"] + 20 * work["Cc"], "render_bwd": 24 * work["E_b"] + 95 * work["Cc"]}
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-
-    roofline = None
-    stages = None
-    if args.impl == "ours" and not args.no_stage_profile:  # every rank runs it (ranks stay in step); rank 0 reports
+    roofline = stages = micro = None
+    if not args.no_stage_profile:  # every rank runs it (ranks stay in step); rank 0 reports
         if dist is not None:
             torch.cuda.synchronize()
             dist.barrier()
+        micro = Dmod.microbench()
         L.gsr_set_profiling(1)
         acc = {}
         nprof = max(3, min(10, args.steps))
         for _ in range(nprof):
-            zero_grads()
-            rs = settings_for(pkg, wl["cams"][0], bg, device)
-            means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-            color, radii, depth, alpha, segment = rasterize(leaves, means2D, rs)
-            torch.autograd.backward([color, depth], [ug["color"], ug["depth"]])
+            rs = make_settings(GS, cams[0], bg)
+            if fwd_only:
+                with torch.no_grad():
+                    render_parts(rs)
+            else:
+                zero_grads()
+                means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+                color, radii, depth, alpha, segment = rasterize(rs, means2D)
+                torch.autograd.backward([color, depth], [ug["color"], ug["depth"]])
             torch.cuda.synchronize()
             for k, v in pkg._lib.stage_times().items():
                 acc[k] = acc.get(k, 0.0) + v / nprof
         L.gsr_set_profiling(0)
-        if os.environ.get("GSR_BENCH_DEBUG"):
-            print("DEBUG rank", rank, "stages", {k: round(v, 4) for k, v in acc.items()}, file=sys.stderr, flush=True)
         group = {"preprocess_fwd": ["preprocess_fwd"], "binning": ["depth_sort", "emit", "tile_sort", "tile_ranges"], "render_fwd": ["render_fwd"],
-                 "render_bwd": ["render_bwd"], "preprocess_bwd": ["preprocess_bwd"]}
+                 "render_bwd": ["render_bwd"], "preprocess_bwd": ["preprocess_bwd"], "grad_fills": ["grad_fills"]}
         stages = {}
         for gname, members in group.items():
             ms = sum(acc.get(m, 0.0) for m in members)
-            stages[gname] = {"ms": round(ms, 4), "alg_bytes": B[gname], "GBps": round(B[gname] / (ms * 1e-3) / 1e9, 1) if ms > 0 else None,
-                             "frac_hbm": round(B[gname] / (ms * 1e-3) / 1e9 / hbm_peak, 4) if ms > 0 else None}
-        dom = max(stages, key=lambda k: stages[k]["ms"])
-        ach = stages[dom]["GBps"]
-        traffic = None  # dram bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-        try:
-            kern = json.load(open(os.path.join(ROOT, "profiles", "r01_kernels.json")))
+            if ms <= 0:
+                continue
+            st = {"ms": round(ms, 4), "alg_bytes": B[gname], "GBps": round(B[gname] / (ms * 1e-3) / 1e9, 1),
+                  "frac_hbm": round(B[gname] / (ms * 1e-3) / 1e9 / peak, 4)}
+            if gname in flops:
+                st["alg_flops"] = flops[gname]
+                st["TFLOPs"] = round(flops[gname] / (ms * 1e-3) / 1e12, 3)
+                st["frac_fp32"] = round(st["TFLOPs"] / micro["ffma_tflops"], 4) if micro["ffma_tflops"] else None
+            if gname == "grad_fills":
+                st["note"] = "cudaMemsetAsync of the dense gradient rows on a side stream, concurrent with render_bwd"
+            stages[gname] = st
+        dom = max((k for k in stages if k != "grad_fills"), key=lambda k: stages[k]["ms"])
+        traffic, traffic_src = None, None
+        try:  # dram bytes per launch of the dominant kernel, from the newest committed `ncu --set full` summary
+            cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_kernels.json"))
+            kern = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
             for kname, kv in kern.items():
-                if dom in kname and "_kernel" in kname:  # render_bwd -> render_bwd2_kernel<2> / render_bwd_kernel<2>
-                    traffic = kv.get("dram_traffic_bytes")
+                if dom.replace("_", "") in kname.replace("_", "") and "_kernel" in kname and kv.get("workload", "cfg3") == name.replace("cfg4", "cfg3"):
+                    traffic, traffic_src = kv.get("dram_traffic_bytes"), "profiles/%s: %s" % (cands[-1], kname)
         except Exception:
             pass
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
-                    "traffic": traffic, "peak_source": peak_src, "launch_ms": stages[dom]["ms"], "alg_bytes_per_launch": B[dom],
-                    "note": "compositing is FP32-issue / shared-memory / atomic bound, not HBM bound (no stage is a dense contraction); "
-                            "the HBM fraction is reported because the contract asks for it, see DESIGN.md"}
-    elif args.impl == "reference":
-        ach = bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9
-        roofline = {"kernel": "whole step (reference CUDA)", "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src}
+        if dom in flops:
+            roofline = {"kernel": dom, "bound": "fp32-issue", "achieved": stages[dom]["TFLOPs"], "peak": round(micro["ffma_tflops"], 2),
+                        "unit": "TFLOP/s", "frac": stages[dom]["frac_fp32"], "traffic": traffic, "traffic_source": traffic_src,
+                        "launch_ms": stages[dom]["ms"], "alg_flops_per_launch": flops[dom],
+                        "flop_model": "render_bwd = 24 E_b + 95 Cc, render_fwd = 21 E + 20 Cc (SURVEY.md 8d; E, E_b, Cc counted by gsr_count_work "
+                                      "from the bit-exact ranges / n_contrib state, see config.stats)",
+                        "peak_source": "FFMA chain micro-benchmark run in this process (gsr_microbench, 3-register form); see `microbench`",
+                        "hbm_note": {"alg_bytes_per_launch": B[dom], "GBps": stages[dom]["GBps"], "frac_hbm": stages[dom]["frac_hbm"], "peak_GBps": peak,
+                                     "why_not_hbm": "the per-tile lists are served from L2 (DRAM traffic << algorithmic bytes); the kernel is "
+                                                    "bound by instruction issue (FP32 + MUFU + shared memory + red.global)"}}
+        else:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac_hbm"],
+                        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": stages[dom]["ms"],
+                        "alg_bytes_per_launch": B[dom]}
 
     if px is not None:
         px.close()
@@ -583,58 +848,65 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and nranks == 1:
-        cpu_baseline = run_cpu_baseline(syn, args.workload)
-    if args.impl == "reference":
-        cpu_baseline = {"value": round(value, 4), "unit": "it/s", "cores": 0, "kind": "reference",
-                        "sample": "full %s on the GPU: the reference's own implementation of this path is CUDA (oracle/_ref/ref_dgr_C.so), "
-                                  "it ships no CPU path" % args.workload}
+        cpu_baseline = run_cpu_baseline(syn, name, fwd_only=fwd_only)
 
+    unit = "frames/s" if fwd_only else "it/s"
+    if fwd_only:
+        what = "GaussianRasterizer.forward_parts: 4 resident sub-scenes of %d Gaussians rendered without concatenation, forward only" % (P // 4)
+    else:
+        what = "rasterize_gaussians fwd (colour+depth+alpha+segment) + bwd (dL/dcolour, dL/ddepth)"
+    exch = ""
+    if nranks > 1:
+        exch = {"peer": ", gradient exchange = peer memory: every rank's gather kernel pulls all ranks' packets of the visible Gaussians over NVLink "
+                        "while summing them into the flat buffer (one stream-ordered barrier, no all-gather)",
+                "packets": ", gradient exchange = one NCCL all-gather of per-view blobs (packets of the visible Gaussians + visibility index), then "
+                           "one gather pass into the flat buffer",
+                "dense": ", gradients accumulated in one flat buffer (61 floats/Gaussian), one NCCL all-reduce"}[mode]
     line = {
-        "metric": "train-step it/s (fwd+bwd, 1080p, 6M gaussians)" if args.workload in ("cfg3", "cfg4") else "train-step it/s (fwd+bwd)",
-        "value": round(value, 4), "unit": "it/s", "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRICS[name], "value": round(value, 4), "unit": unit, "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d Gaussians SH3, %dx%d, rasterize_gaussians fwd (colour+depth+alpha+segment) + bwd (dL/dcolour, dL/ddepth), "
-                               "%d view(s)/rank/step%s" % (args.workload, P, W, Hh, V,
-                                                           (", gradient exchange = peer memory: every rank's gather kernel pulls all ranks' 68-B packets of the visible Gaussians over "
-                                                            "NVLink while summing them into the flat buffer (one stream-ordered barrier, no all-gather)" if use_peer else
-                                                            ", gradient exchange = one NCCL all-gather of per-view blobs (68-B packets of the visible Gaussians + "
-                                                            "visibility index), then one gather pass into the flat buffer" if use_packets else
-                                                            ", gradients accumulated in one flat buffer (61 floats/Gaussian), one NCCL all-reduce")
-                                                           if nranks > 1 else ""),
-                   "views_per_rank": V, "l2": "inputs (%.2f GB of parameters) are larger than the 126 MB L2" % (61 * 4 * P / 1e9), "stats": stats,
+        "config": {"workload": "%s: %d Gaussians SH3, %dx%d, %s, %d view(s)/step = %d view(s)/rank/step%s" % (name, P, W, Hh, what, V * nranks, V, exch),
+                   "views_per_step": V * nranks, "views_per_rank": V,
+                   "l2": "inputs (%.2f GB of parameters) are larger than the 126 MB L2" % (61 * 4 * P / 1e9), "stats": stats,
                    "alg_bytes_per_step": bytes_step},
-        "e2e": {"value": round(e2e_value, 4), "unit": "it/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": round(ms_e2e / args.steps, 4), "loss": loss_host[0]},
-        "gpu_launches": launches_timed if args.impl == "ours" else 0,
+        "e2e": {"value": round(e2e_value, 4), "unit": unit, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": round(ms_e2e / args.steps, 4), "loss": loss_host[0],
+                "loss_fn": "rendered image read back to pinned host memory" if fwd_only else "L1 colour + depth supervision: " + depth_loss_name},
+        "gpu_launches": launches_timed,
         "clocks": clocks,
         "roofline": roofline,
-        "roofline_step": {"alg_bytes": bytes_step, "achieved": round(bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9, 1), "peak": hbm_peak,
-                          "unit": "GB/s", "frac": round(bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9 / hbm_peak, 4)},
+        "roofline_step": {"alg_bytes": bytes_step, "achieved": round(bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9, 1), "peak": peak,
+                          "unit": "GB/s", "frac": round(bytes_step / (ms_dev / args.steps / V * 1e-3) / 1e9 / peak, 4)},
         "cpu_baseline": cpu_baseline,
-        "step_ms": step_stats,
+        "step_ms": timer.stats,
         "fwd_ms_per_frame": round(fwd_ms, 4),
     }
+    if micro is not None:
+        line["microbench"] = micro
+    if cfg4_1gpu is not None:
+        line["cfg4_1gpu"] = cfg4_1gpu
+    if exchange_parity is not None:
+        line["exchange_parity"] = exchange_parity
     if comm_ms is not None:
-        gbytes = 61 * 4 * P / 1e9
-        if use_peer:
-            line["collective"] = {"op": "4-byte ncclAllReduce as stream-ordered barrier + ONE gather kernel over %d views reading peer blobs "
-                                        "over NVLink (68 B per visible Gaussian + 2 index words per 32 Gaussians per view)" % (nranks * V),
-                                  "bytes_pulled_per_rank": int((68 * stats["V"] + P // 4) * V * (nranks - 1)), "ms": round(comm_ms, 3),
-                                  "dense_allreduce_bytes": int(61 * 4 * P)}
-        elif use_packets:
-            line["collective"] = {"op": "count all-gather + ONE ncclAllGather of view blobs (68 B per visible Gaussian + 2 index words per 32 "
-                                        "Gaussians) + ONE gather pass over %d views that writes every dense row once" % (nranks * V),
-                                  "bytes_sent_per_rank": int((68 * xstate.get("cap", stats["V"]) + P // 4) * V), "ms": round(comm_ms, 3),
+        pw = Dmod.PACKET_WORDS if hasattr(Dmod, "PACKET_WORDS") else 17
+        if mode == "peer":
+            pulled = int((4 * pw * stats["V"] + P // 4) * V * (nranks - 1))
+            line["collective"] = {"op": "4-byte ncclAllReduce as stream-ordered barrier + ONE gather kernel over %d views reading peer blobs over "
+                                        "NVLink (%d B per visible Gaussian + 2 index words per 32 Gaussians per view)" % (nranks * V, 4 * pw),
+                                  "bytes_pulled_per_rank": pulled, "ms": round(comm_ms, 3),
+                                  "nvlink_GBps_in": round(pulled / (comm_ms * 1e-3) / 1e9, 1), "dense_allreduce_bytes": int(61 * 4 * P)}
+        elif mode == "packets":
+            line["collective"] = {"op": "count all-gather + ONE ncclAllGather of view blobs + ONE gather pass over %d views" % (nranks * V),
+                                  "bytes_sent_per_rank": int((4 * pw * xstate.get("cap", stats["V"]) + P // 4) * V), "ms": round(comm_ms, 3),
                                   "dense_allreduce_bytes": int(61 * 4 * P)}
         else:
+            gbytes = 61 * 4 * P / 1e9
             line["collective"] = {"op": "1 x ncclAllReduce(sum, fp32) of the flat gradient buffer", "bytes": int(61 * 4 * P),
                                   "ms": round(comm_ms, 3), "algbw_GBps": round(gbytes / (comm_ms * 1e-3), 1),
                                   "busbw_GBps": round(gbytes / (comm_ms * 1e-3) * 2 * (nranks - 1) / nranks, 1)}
     if stages is not None:
         line["stages"] = stages
-    if args.impl == "reference":
-        line["impl"] = "reference"
     out.write(json.dumps(line) + "\n")
     out.flush()
     if dist is not None:
@@ -643,9 +915,9 @@ def main():
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def run_cpu_baseline(syn, workload, row_stride=1):
+def run_cpu_baseline(syn, workload, row_stride=1, fwd_only=False):
     """Oracle B (C + OpenMP, all host cores) on a bounded sample of the SAME workload: full per-Gaussian stages and binning,
-    compositing forward+backward on every `row_stride`-th tile row; the compositing time is scaled by the sampled
+    compositing forward(+backward) on every `row_stride`-th tile row; the compositing time is scaled by the sampled
     fraction of tile instances. Reported baseline, not a target."""
     from oracle import cpu_oracle as O
 
@@ -655,6 +927,8 @@ def run_cpu_baseline(syn, workload, row_stride=1):
     n = lambda t: t.numpy()
     O.lib()
     gy = (Hh + 15) // 16
+    if P * W * Hh > 6_000_000 * 1920 * 1080:  # cfg5: keep the sample within ~10-30 s of CPU work
+        row_stride = max(row_stride, 4)
     row_stride = min(row_stride, gy)
     reps, t_f, t_b = 0, 0.0, 0.0
     while reps < 1 or (t_f + t_b < 10.0 and reps < 5):  # about 10 s of CPU work, averaged
@@ -663,20 +937,19 @@ def run_cpu_baseline(syn, workload, row_stride=1):
                        n(cam["campos"]), np.zeros(3, np.float32), shs=n(gs["shs"]), segments=n(gs["segments"]), scales=n(gs["scales"]),
                        rotations=n(gs["rotations"]), row_stride=row_stride, row_offset=row_stride // 2)
         t1 = time.time()
-        O.backward(st, n(ug["color"]), n(ug["depth"]))
+        if not fwd_only:
+            O.backward(st, n(ug["color"]), n(ug["depth"]))
         t_f += t1 - t0
         t_b += time.time() - t1
         reps += 1
-    t0, t1, t2 = 0.0, t_f / reps, (t_f + t_b) / reps
+    t1, t2 = t_f / reps, (t_f + t_b) / reps
     total_cpu_s = t_f + t_b
     # fraction of tile instances in the sampled rows
     gx = (W + 15) // 16
     rng = st["ranges"].astype(np.int64)
     lens = (rng[:, 1] - rng[:, 0]).reshape(gy, gx).sum(1)
     frac = float(lens[row_stride // 2::row_stride].sum()) / max(1.0, float(lens.sum()))
-    # split: per-Gaussian + binning parts run in full, compositing parts are sampled. Time them separately by a second,
-    # compositing-free estimate: t_full_parts = total - t_sampled_compositing is not separable without extra timers, so
-    # re-run the sampled compositing alone to measure it.
+    # per-Gaussian + binning parts run in full, compositing parts are sampled: re-run the sampled compositing alone to split them
     L = O.lib()
     tc0 = time.time()
     nc = np.zeros(W * Hh, np.uint32)
@@ -684,36 +957,65 @@ def run_cpu_baseline(syn, workload, row_stride=1):
     L.orc_render_forward(O._i(W), O._i(Hh), O._i(2), O._p(st["ranges"]), O._p(st["point_list"]), O._p(st["means2D"]), O._p(st["rgb"]),
                          O._p(st["_inputs"]["segments"]), O._p(st["depths"]), O._p(st["conic_opacity"]), O._p(np.zeros(3, np.float32)), O._p(col),
                          O._p(seg), O._p(dep), O._p(alp), O._p(nc), O._i(row_stride), O._i(row_stride // 2))
-    tc1 = time.time()
-    t_render_fwd_s = tc1 - tc0
-    t_fwd_full_parts = max(0.0, (t1 - t0) - t_render_fwd_s)
-    # backward: compositing dominates the sampled part; preprocess backward runs in full. Estimate the split with the same ratio
-    # measured on the forward would be wrong, so time preprocess_backward-only by calling backward on a state with empty ranges.
-    st_empty = dict(st)
-    st_empty["ranges"] = np.zeros_like(st["ranges"])
-    tb0 = time.time()
-    O.backward(st_empty, n(ug["color"]), n(ug["depth"]))
-    tb1 = time.time()
-    t_bwd_full_parts = tb1 - tb0
-    t_render_bwd_s = max(0.0, (t2 - t1) - t_bwd_full_parts)
+    t_render_fwd_s = time.time() - tc0
+    t_fwd_full_parts = max(0.0, t1 - t_render_fwd_s)
+    t_bwd_full_parts = t_render_bwd_s = 0.0
+    if not fwd_only:  # preprocess backward alone: backward on a state with empty ranges
+        st_empty = dict(st)
+        st_empty["ranges"] = np.zeros_like(st["ranges"])
+        tb0 = time.time()
+        O.backward(st_empty, n(ug["color"]), n(ug["depth"]))
+        t_bwd_full_parts = time.time() - tb0
+        t_render_bwd_s = max(0.0, (t2 - t1) - t_bwd_full_parts)
     est = t_fwd_full_parts + t_bwd_full_parts + (t_render_fwd_s + t_render_bwd_s) / max(frac, 1e-9)
-    return {"value": round(1.0 / est, 5), "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "%s scene; per-Gaussian stages, key emit, sort and ranges in full; compositing fwd+bwd on every %dth tile row "
+    return {"value": round(1.0 / est, 5), "unit": "frames/s" if fwd_only else "it/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%s scene; per-Gaussian stages, key emit, sort and ranges in full; compositing %s on every %dth tile row "
                       "(%.1f%% of tile instances), scaled; %d repetition(s), %.1f s of CPU work measured, %.1f s per step"
-                      % (workload, row_stride, 100 * frac, reps, total_cpu_s, est),
+                      % (workload, "fwd" if fwd_only else "fwd+bwd", row_stride, 100 * frac, reps, total_cpu_s, est),
             "measured_s": round(total_cpu_s, 2)}
 
 
 def reference_cpu_port(args, syn, out):
     """Fallback of `--impl reference` when the reference CUDA build (oracle/_ref) or a GPU is unavailable: the C port."""
-    cb = run_cpu_baseline(syn, args.workload)
-    line = {"metric": "train-step it/s (fwd+bwd, 1080p, 6M gaussians)", "value": cb["value"], "unit": "it/s", "n_gpus": 0, "steps": 1, "warmup": 0,
+    name = args.workload or "cfg3"
+    cb = run_cpu_baseline(syn, name, fwd_only=name == "cfg5")
+    line = {"metric": METRICS[name], "value": cb["value"], "unit": cb["unit"], "n_gpus": 0, "steps": 1, "warmup": 0,
             "ms_per_step": round(1e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload}, "impl": "reference", "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "data": "synthetic", "config": {"workload": name}, "impl": "reference", "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     out.write(json.dumps(line) + "\n")
     out.flush()
     return 0
+
+
+def main():
+    out = _claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="default: cfg3 at N = 1 (the headline configuration), cfg4 at N > 1 (8 views/step sharded over the ranks)")
+    ap.add_argument("--views-per-step", type=int, default=0, help="B views per step sharded over the ranks (strong scaling)")
+    ap.add_argument("--views-per-rank", type=int, default=0, help="V views per rank per step (weak scaling); overrides --views-per-step")
+    ap.add_argument("--grad-exchange", default="peer", choices=["peer", "packets", "dense"],
+                    help="N>1: peer = gather kernel pulls every rank's gradient packets over NVLink peer memory (default); "
+                         "packets = NCCL all-gather of the packets, then the gather kernel; dense = all-reduce of the flat buffer")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage-profile", action="store_true")
+    ap.add_argument("--no-cfg4-base", action="store_true", help="skip the 8-views-per-step single-GPU measurement of the default N = 1 run")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if world > 1 and rank != 0:
+            return 0  # the reference is single-GPU: rank 0 alone runs and prints it
+        if args.workload is None:
+            args.workload = "cfg3"
+        return reference_arm(args, out)
+    return ours_arm(args, out)
 
 
 if __name__ == "__main__":

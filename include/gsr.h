@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 2
+#define GSR_ABI_VERSION 3
 
 #define GSR_OK 0
 #define GSR_ERR_INVALID_ARGUMENT (-1)
@@ -92,7 +92,16 @@ typedef struct GsrGaussians {
      * subset_count. Not combined with gsr_backward_packets. */
     const int32_t* subset;
     int32_t subset_count;
+    /* Sub-scene fusion without concatenation. The reference's viewer merges sub-scenes by concatenating every
+     * attribute array (visualizer.py:196-226, _merge_scenes: np.concatenate of xyz, features, opacities, segments, rots, scales).
+     * num_parts > 0 renders parts[0], parts[1], ... as ONE scene in that order -- Gaussian i of the fused scene is row
+     * i - start(k) of part k -- straight from the parts' own tensors: P must equal the sum of parts[k].P, the top-level data
+     * pointers are ignored, every part provides the same set of members, and the result is bit-identical to rendering the
+     * concatenated tensors. Render-only (gsr_backward rejects it); not combined with raw_params or subset. */
+    const struct GsrGaussians* parts;
+    int32_t num_parts;
 } GsrGaussians;
+#define GSR_MAX_PARTS 16
 
 /* Forward outputs; every element is written by the kernels (no pre-zeroing needed) when P > 0. */
 typedef struct GsrOutputs {
@@ -108,6 +117,8 @@ typedef struct GsrState {
     void* binning;
     void* img;
     int32_t num_rendered; /* R, as returned by gsr_forward */
+    int32_t num_visible;  /* V of THAT forward (gsr_last_num_visible() right after it), or 0 when unknown: lets
+                             gsr_backward_packets refuse a packet buffer that is too small instead of dropping packets */
 } GsrState;
 
 typedef struct GsrPixelGrads {
@@ -156,8 +167,10 @@ int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* rad
  *   word 7      dL/dopacity     words 8-9  dL/dsegment     words 10-12  dL/dscale     words 13-16  dL/drotation
  * 68 B instead of the 244-B dense row: the 48-float SH gradient row is rank one, basis(view direction) x dL/dRGB, and is
  * rebuilt by gsr_apply_packets on the receiving rank from the Gaussian's position and that view's camera centre.
- * Packets are ordered by Gaussian id; *count_dev receives the number of visible Gaussians (packets beyond `capacity` are
- * dropped -- size it with gsr_last_num_visible()). dL_dmeans2D (optional, dense [P,3]) is overwritten for the
+ * Packets are ordered by Gaussian id; *count_dev receives the number of visible Gaussians. `capacity` must be >= the number of
+ * visible Gaussians of the forward the state belongs to: with state->num_visible set, a smaller buffer fails with
+ * GSR_ERR_OVERFLOW before anything is launched (with num_visible == 0 = unknown, packets beyond `capacity` are dropped and
+ * *count_dev tells). dL_dmeans2D (optional, dense [P,3]) is overwritten for the
  * densification statistics. Requires shs + scales/rotations (the training configuration). */
 #define GSR_PACKET_WORDS 17
 int gsr_backward_packets(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
@@ -209,6 +222,7 @@ typedef struct GsrAdamGroup {
     uint64_t offset;
     uint64_t count;
     float lr;
+    int32_t step; /* > 0: this group's own 1-based step number (torch.optim.Adam counts steps per parameter); 0: use `step` */
 } GsrAdamGroup;
 int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const GsrAdamGroup* groups, int32_t num_groups,
                   double beta1, double beta2, double eps, int32_t step, gsr_stream_t stream);
@@ -261,6 +275,27 @@ int gsr_export_state(int32_t P, int32_t image_width, int32_t image_height, const
  * gsr_set_profiling(1) is active (adds cudaEvent records; used by bench.py for the roofline block). */
 /* Number of CUDA kernels this library has launched so far in this process (all threads). */
 unsigned long long gsr_launch_count(void);
+
+/* ---- measurement support (bench.py, tests; not on the product path) ----
+ * gsr_microbench: achievable rates of the instruction classes that bound the compositing kernels, measured on the current device
+ * with CUDA events on `stream` (blocks until done, ~20 ms): dependent-chain-free FFMA (3-register form), packed FFMA2
+ * (fma.rn.f32x2), MUFU.EX2, SHFL, and the backward's atomic pattern (12 consecutive floats of one 48-byte record per warp
+ * instruction, records spread over an L2-resident table). SURVEY.md 8d item 2. */
+typedef struct GsrMicrobench {
+    float ffma_tflops;   /* 2 flop per lane-op */
+    float ffma2_tflops;  /* 4 flop per lane-op */
+    float ex2_gops;      /* 1e9 lane-ops / s */
+    float shfl_gops;     /* 1e9 lane-ops / s */
+    float red_gops;      /* 1e9 float atomics / s */
+    float sm_clock_mhz_nominal;
+    int32_t sm_count;
+} GsrMicrobench;
+int gsr_microbench(GsrMicrobench* result, gsr_stream_t stream);
+/* gsr_count_work: algorithmic work of a rendered frame, counted by replaying the reference's per-pixel loop (forward.cu:314-377)
+ * over the saved state: counters_dev[0] = E (list entries evaluated until each pixel is done), [1] = Cc (entries that
+ * contributed), [2] = E_b (entries the backward re-traverses = sum of n_contrib). P = rendered Gaussians (subset_count with an
+ * index list). */
+int gsr_count_work(int32_t P, int32_t image_width, int32_t image_height, const GsrState* state, uint64_t* counters_dev, gsr_stream_t stream);
 
 #define GSR_STAGE_COUNT 16
 void gsr_set_profiling(int enable);

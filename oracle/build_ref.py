@@ -90,9 +90,36 @@ def _build(name, srcs, extra, verbose):
     return target
 
 
+# The reference's Python CALLERS of the path (gaussian_renderer.render(), the model and camera classes, the losses) and its own
+# autograd wrapper, copied verbatim into the git-ignored baseline/_ref/refpy/ (shipped to the GPU box by
+# gpurun, never committed). tests/test_reference_callers_gpu.py imports them UNCHANGED -- once over this repo's drop-in
+# `diff_gaussian_rasterization`, once over the reference's own wrapper + ref_dgr_C.so -- and compares everything they return.
+CALLER_FILES = [
+    "gaussian_renderer/__init__.py", "scene/cameras.py", "scene/gaussian_model.py", "utils/graphics_utils.py", "utils/general_utils.py",
+    "utils/sh_utils.py", "utils/system_utils.py", "utils/loss_utils.py",
+    "submodules_local/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py",
+]
+CALLERS_OUT = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "refpy")
+
+
+def copy_callers():
+    import shutil
+
+    if not os.path.isdir(REF):
+        return False
+    for rel in CALLER_FILES:
+        src = os.path.join(REF, rel)
+        dst = os.path.join(CALLERS_OUT, rel.replace("submodules_local/diff-gaussian-rasterization/", "ref_wrapper/"))
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not os.path.exists(dst) or os.path.getmtime(src) > os.path.getmtime(dst):
+            shutil.copyfile(src, dst)
+    return True
+
+
 def build(verbose=False):
     if not os.path.isdir(REF):
         return False
+    copy_callers()
     os.makedirs(OUT, exist_ok=True)
     dgr = os.path.join(REF, "submodules_local", "diff-gaussian-rasterization")
     knn = os.path.join(REF, "submodules_local", "simple-knn")

@@ -100,6 +100,25 @@ def test_mark_visible_matches_view_depth():
     assert got.dtype == np.bool_ and (got != exp).mean() <= 1e-4  # fp32 FMA vs non-FMA at the z == 0.2 boundary
 
 
+def test_mark_visible_bit_exact_vs_reference_cuda():
+    """markVisible against the reference's own _C.mark_visible (rasterizer_impl.cu:141-153) on the same device: bit for bit, at
+    a plumbing size and at cfg3 size, for a rotated camera too."""
+    C = H.ref_dgr()
+    if C is None:
+        pytest.skip("oracle/_ref not built")
+    Pk = H.pkg()
+    syn = H.synthetic()
+    for P, seed, yaw in [(50_000, 6, 0.0), (6_000_000, 2, 135.0), (1, 3, 0.0), (257, 4, 45.0)]:
+        gs = syn.make_gaussians(P, seed)
+        cam = syn.make_camera(320, 200, yaw_deg=yaw)
+        m = gs["means3D"].cuda()
+        rs = H.settings(cam, torch.zeros(3))
+        got = Pk.GaussianRasterizer(rs).markVisible(m)
+        exp = C.mark_visible(m, rs.viewmatrix, rs.projmatrix)
+        assert got.dtype == torch.bool and got.shape == exp.shape and torch.equal(got, exp), (P, yaw)
+        assert 0 < int(got.sum()) <= P
+
+
 def test_prefiltered_culled_point_raises():
     gs, cam = _mk(1000, 64, 64, 8)
     rs = H.settings(cam, torch.zeros(3), prefiltered=True)
@@ -245,3 +264,48 @@ def test_gradient_packets_rebuild_dense_rows():
     mv.exchange_packets(D, None, flat, gs, sets2, [campos], 3, world=1, state=st)
     for leaf, nat in names.items():
         assert H.rel_linf(flat.views[leaf], dense[0][nat] + dense[1][nat]) <= 2e-5, leaf
+
+
+def test_packet_capacity_comes_from_the_forward_it_belongs_to():
+    """Several views forwarded before their backwards (or an eval render in between): the packet buffer of a view is sized by
+    THAT view's visible count, and a buffer that is too small is refused (GSR_ERR_OVERFLOW) instead of dropping packets."""
+    import importlib
+
+    Pk = H.pkg()
+    D = Pk.diff_gaussian_rasterization
+    mv = importlib.import_module(H.PKG_NAME + ".multiview")
+    syn = H.synthetic()
+    gs = H.to_dev(syn.make_gaussians(40_000, 21))
+    cam_a, cam_b = syn.make_camera(160, 120), syn.make_camera(160, 120, yaw_deg=90.0, radius=40.0)  # b: far away, few visible
+    rs_a, rs_b = H.settings(cam_a, torch.zeros(3)), H.settings(cam_b, torch.zeros(3))
+    ug = H.to_dev(syn.upstream_grads(160, 120, 5))
+    fwd_a = mv.native_view_forward(D, gs, rs_a)
+    fwd_b = mv.native_view_forward(D, gs, rs_b)  # the thread's "last forward" is now b
+    Va, Vb = int((fwd_a[5] > 0).sum()), int((fwd_b[5] > 0).sum())
+    assert fwd_a[0].num_visible == Va and fwd_b[0].num_visible == Vb and Va > Vb
+    blob, count, nvis = mv.native_view_backward_packets(D, gs, rs_a, fwd_a, ug)
+    assert nvis == Va == int(count.item()) and D.packet_blob_capacity(blob, 40_000) >= Va
+    flat, dense = mv.FlatGradients(40_000, "cuda"), mv.FlatGradients(40_000, "cuda")
+    mv.exchange_packets(D, None, flat, gs, [(blob, count, nvis)], [[cam_a["campos"].cuda()]], 3, world=1)
+    mv.native_view_backward(D, gs, rs_a, fwd_a, ug, dense, first=True)
+    assert H.rel_linf(flat.packed(), dense.packed()) <= 2e-5
+    with pytest.raises(RuntimeError, match="do not fit"):
+        D._backward_packets_native(rs_a, gs["means3D"], fwd_a[5], gs["segments"], gs["scales"], gs["rotations"], ug["color"], None, ug.get("depth"),
+                                   None, gs["shs"], fwd_a[6], fwd_a[0], fwd_a[7], fwd_a[8], fwd_a[4], capacity=max(Va // 2, 1))
+
+
+def test_unaligned_views_of_a_flat_buffer_are_accepted():
+    """Contiguous inputs that start at an odd offset of a larger allocation (the reference's scalar loads accept them)."""
+    Pk = H.pkg()
+    gs, cam = _mk(3000, 96, 64, 12)
+    rs = H.settings(cam, torch.zeros(3))
+    ref = H.run_ours(gs, rs, export=False)
+    shifted = {}
+    for k, v in gs.items():
+        buf = torch.empty(v.numel() + 3, device="cuda")
+        buf[1:1 + v.numel()] = v.reshape(-1)
+        shifted[k] = buf[1:1 + v.numel()].view(v.shape)
+        assert shifted[k].data_ptr() % 16 != 0 and shifted[k].is_contiguous()
+    out = H.run_ours(shifted, rs, export=False)
+    for k in ["color", "depth", "alpha", "segment", "radii"]:
+        assert torch.equal(out[k], ref[k]), k

@@ -22,7 +22,7 @@ def test_libgsr_loads_and_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(lib, sym), "libgsr.so does not export %s" % sym
     assert set(Pk._lib.SYMBOLS) == declared
-    assert lib.gsr_abi_version() == 2
+    assert lib.gsr_abi_version() == Pk._lib.GSR_ABI_VERSION == int(re.search(r"#define GSR_ABI_VERSION (\d+)", header).group(1))
     assert lib.gsr_backward_scratch_bytes(1000) >= 1024 * 48 and lib.gsr_backward_scratch_bytes(0) == 0
 
 

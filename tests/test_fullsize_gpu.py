@@ -92,3 +92,84 @@ def test_cfg3_backward_linearity_and_packet_exchange(cfg3):
     assert H.rel_linf(flat.packed(), two.packed()) <= 2e-5
     vis = fwd[5] > 0
     assert float(flat.views["shs"][~vis].abs().max()) == 0.0 and float(flat.views["means3D"][~vis].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------- cfg2 and cfg5
+def _assert_state_equal(ours, ref):
+    assert ours["num_rendered"] == ref["num_rendered"] > 0
+    assert torch.equal(ours["radii"], ref["radii"])
+    so, sr = ours["state"], ref["state"]
+    assert torch.equal(so["point_keys"], sr["point_keys"]) and torch.equal(so["point_list"], sr["point_list"])
+    assert torch.equal(so["ranges"], sr["ranges"]) and torch.equal(so["n_contrib"], sr["n_contrib"])
+    assert torch.equal(so["tiles_touched"], sr["tiles_touched"])
+
+
+def test_cfg2_full_parity_vs_reference_cuda():
+    """BASELINE.json configs[1] at full size (3 M Gaussians, 1297x840 -- not a multiple of the tile size), forward + backward
+    against the reference CUDA build: integer state bit-exact, images <= 1e-5, gradients <= 1e-4 relative."""
+    if H.ref_dgr() is None:
+        pytest.skip("oracle/_ref not built")
+    syn = H.synthetic()
+    P, W, Hh, seed = syn.CONFIGS["cfg2"]
+    gs, cam = syn.make_scene("cfg2")
+    ug = H.to_dev(syn.upstream_grads(W, Hh, seed, with_depth=True, with_segment=True, with_alpha=True))
+    gs = H.to_dev(gs)
+    rs = H.settings(cam, torch.tensor([0.2, 0.1, 0.3]))
+    ours = H.run_ours(gs, rs, ug)
+    ref = H.run_ref(gs, rs, ug)
+    torch.cuda.synchronize()
+    _assert_state_equal(ours, ref)
+    for k in ["color", "depth", "alpha", "segment"]:
+        assert float((ours[k] - ref[k]).abs().max()) <= 1e-5, k
+    for k in ["means3D", "means2D", "sh", "segments", "opacities", "scales", "rotations"]:
+        a, b = ours["grads"][k], ref["grads"][k]
+        assert H.rel_linf(a, b.reshape(a.shape)) <= 1e-4, k
+
+
+def test_cfg5_forward_parity_and_fused_parts():
+    """BASELINE.json configs[4] at full size (10 M Gaussians in four sub-scenes, 3840x2160, forward only): the concatenated scene
+    against the reference CUDA build (integer state bit-exact, images <= 1e-5), and the concatenation-free multi-part entry
+    (GsrGaussians.parts) bit-identical to rendering the concatenated tensors."""
+    Pk = H.pkg()
+    D = Pk.diff_gaussian_rasterization
+    syn = H.synthetic()
+    P, W, Hh, seed = syn.CONFIGS["cfg5"]
+    parts = [H.to_dev(syn.make_gaussians(P // 4, seed + i, scale_P=P)) for i in range(4)]
+    cam = syn.make_camera(W, Hh)
+    rs = H.settings(cam, torch.tensor([0.0, 0.0, 0.0]))
+    with torch.no_grad():
+        fused = D._forward_parts_native(parts, rs)
+        gs = {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+        scene, _ = syn.make_scene("cfg5")
+        assert torch.equal(gs["means3D"].cpu(), scene["means3D"])  # the recipe's merged scene
+        del scene
+        ours = H.run_ours(gs, rs)
+    for i, k in enumerate(["num_rendered", "color", "depth", "segment", "alpha", "radii"]):
+        a, b = fused[i], ours[k]
+        assert (a == b) if k == "num_rendered" else torch.equal(a, b), k
+    st = D.export_state(P, W, Hh, fused[6], fused[7], fused[8], fused[0])
+    assert torch.equal(st["point_list"], ours["state"]["point_list"]) and torch.equal(st["n_contrib"], ours["state"]["n_contrib"])
+    del fused, st
+    rast = Pk.GaussianRasterizer(rs)
+    c2 = rast.forward_parts(parts)[0]
+    assert torch.equal(c2, ours["color"])
+    if H.ref_dgr() is None:
+        pytest.skip("oracle/_ref not built: fused == concatenated checked, reference comparison skipped")
+    with torch.no_grad():
+        ref = H.run_ref(gs, rs)
+    torch.cuda.synchronize()
+    _assert_state_equal(ours, ref)
+    for k in ["color", "depth", "alpha", "segment"]:
+        assert float((ours[k] - ref[k]).abs().max()) <= 1e-5, k
+
+
+def test_count_work_matches_state(cfg3):
+    """gsr_count_work (the roofline's work counters): E_b equals the sum of n_contrib, Cc <= E_b <= E <= 256 R, and every counted
+    quantity is reproduced by a second run."""
+    gs, cam, ug, rs, (P, W, Hh) = cfg3
+    D = H.pkg().diff_gaussian_rasterization
+    out = H.run_ours(gs, rs)
+    w = D.count_work(P, W, Hh, out["geom"], out["binning"], out["img"], out["num_rendered"])
+    assert w["E_b"] == int(out["state"]["n_contrib"].to(torch.int64).sum())
+    assert 0 < w["Cc"] <= w["E_b"] <= w["E"] <= 256 * out["num_rendered"]
+    assert w == D.count_work(P, W, Hh, out["geom"], out["binning"], out["img"], out["num_rendered"])

@@ -77,7 +77,7 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
            "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
-           "gsr_peer_free", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible", "gsr_microbench", "gsr_count_work"]
+           "gsr_peer_free", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible", "gsr_microbench", "gsr_count_work", "gsr_depth_loss", "gsr_depth_loss_scratch_bytes"]
 GSR_ABI_VERSION = 3  # include/gsr.h
 GSR_PACKET_WORDS = 17
 GSR_PEER_HANDLE_BYTES = 64
@@ -134,6 +134,11 @@ def lib():
     L.gsr_image_loss.restype = ctypes.c_int
     L.gsr_image_loss.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.gsr_depth_loss_scratch_bytes.restype = ctypes.c_size_t
+    L.gsr_depth_loss_scratch_bytes.argtypes = [ctypes.c_int64]
+    L.gsr_depth_loss.restype = ctypes.c_int
+    L.gsr_depth_loss.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.gsr_select_rows.restype = ctypes.c_int
     L.gsr_select_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                   ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),

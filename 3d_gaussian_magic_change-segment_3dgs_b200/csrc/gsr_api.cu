@@ -2,6 +2,7 @@
 // Host logic mirrors CudaRasterizer::Rasterizer::forward/backward (cuda_rasterizer/rasterizer_impl.cu:198-458)
 // and the torch glue of rasterize_points.cu:35-242, without torch: raw device pointers + a stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -340,9 +341,11 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     GSR_CUDA(cudaMemcpyAsync(hs->pinned, g.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     GSR_CUDA(cudaEventRecord(hs->ev, s));
 
-    launch_depth_keys(g, s);
+    // depth sort workspace: digit totals, tickets and look-back words of its four single-kernel passes, zeroed in one memset
+    GSR_CUDA(cudaMemsetAsync(g.dhist, 0, g.dhist_words * sizeof(uint32_t), s));
+    launch_depth_keys(g, g.dhist, s);
     GSR_LAUNCHED(s, debug, "depth_keys");
-    int dres = radix_sort_pairs(g.dkeys, g.dvals, g.slots, 32, g.dhist, g.dhist_words, s, g.counters + CNT_VISIBLE);
+    int dres = radix_sort_pairs_lookback(g.dkeys, g.dvals, g.slots, 32, g.dhist, g.dhist_words, true, s, g.counters + CNT_VISIBLE);
     if (dres < 0) return dres;
     GSR_LAUNCHED(s, debug, "depth_sort");
     const uint32_t* sorted_slots = g.dvals[dres];
@@ -363,32 +366,33 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     const uint32_t R = (uint32_t)R64;
     if (num_rendered) *num_rendered = (int32_t)R;
 
+    const int tile_bits = ceil_log2(T) < 1 ? 1 : ceil_log2(T);
     BinState b;
-    const size_t bin_bytes = bin_layout(nullptr, V, R, b);
+    const size_t bin_bytes = bin_layout(nullptr, V, R, tile_bits, b);
     char* bin_base = (char*)alloc(alloc_user, GSR_BUF_BINNING, bin_bytes);
     if (!bin_base) {
         set_error("binning state allocation failed (%zu B)", bin_bytes);
         return GSR_ERR_ALLOC;
     }
-    bin_layout(bin_base, V, R, b);
+    bin_layout(bin_base, V, R, tile_bits, b);
     g_timer.mark(s, "depth_sort");
 
     // ---- instances in depth order, then stable sort by tile ----
-    rc = launch_instance_offsets(g, b, V, sorted_slots, s);
+    GSR_CUDA(cudaMemsetAsync(b.hist, 0, b.zero_bytes, s)); // tile-sort digit totals / tickets / look-back words + the scan's
+    rc = launch_instance_offsets(g, b, V, R, sorted_slots, s);
     if (rc) return rc;
     GSR_LAUNCHED(s, debug, "instance_offsets");
-    const int tile_bits = ceil_log2(T) < 1 ? 1 : ceil_log2(T);
     const int tpasses = radix_num_passes(tile_bits);
     // choose the starting buffers so that the final pass lands in point_list (offset 0 of the binning state)
     uint32_t* tvals[2];
     uint32_t* tkeys[2] = {b.tkeys[0], b.tkeys[1]};
     if (tpasses % 2 == 0) { tvals[0] = b.point_list; tvals[1] = b.vals_alt; }
     else { tvals[0] = b.vals_alt; tvals[1] = b.point_list; }
-    rc = launch_emit(g, b, V, R, sorted_slots, gx, tkeys[0], tvals[0], s);
+    rc = launch_emit(g, b, V, R, sorted_slots, gx, radix_digit_bits(tile_bits), tpasses, b.hist, tkeys[0], tvals[0], s);
     if (rc) return rc;
     GSR_LAUNCHED(s, debug, "emit");
     g_timer.mark(s, "emit");
-    int tres = radix_sort_pairs(tkeys, tvals, R, tile_bits, b.hist, b.hist_words, s);
+    int tres = radix_sort_pairs_lookback(tkeys, tvals, R, tile_bits, b.hist, b.hist_words, true, s);
     if (tres < 0) return tres;
     GSR_LAUNCHED(s, debug, "tile_sort");
     if (R > 0 && tvals[tres] != b.point_list) {
@@ -620,18 +624,26 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     if (!in->scales) { pb.out.dL_dscales = nullptr; pb.out.dL_drotations = nullptr; }
 
     g_timer.begin(s);
-    // fork: the dense zero fills of the output gradients (HBM-write bound, ~1.9 GB) overlap the compositing backward (issue bound)
+    // The dense zero fills of the output gradients (HBM-write bound, ~1.5 GB at cfg3) are independent of the compositing backward
+    // (issue bound). GSR_FILL_STREAM=side (default) forks them onto a side stream so that they overlap it; =main runs them on the
+    // launching stream after it (A/B: profiles/).
+    static const bool fills_on_side = !(getenv("GSR_FILL_STREAM") && !strcmp(getenv("GSR_FILL_STREAM"), "main"));
     SideStream* ss = side_stream();
     if (!ss) return GSR_ERR_CUDA;
-    GSR_CUDA(cudaEventRecord(ss->fork, s));
-    GSR_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-    if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t0, ss->stream));
-    rc = launch_grad_fills(pb, ss->stream);
-    if (rc) return rc;
-    if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t1, ss->stream));
-    GSR_CUDA(cudaEventRecord(ss->join, ss->stream));
+    if (fills_on_side) {
+        GSR_CUDA(cudaEventRecord(ss->fork, s));
+        GSR_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+        if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t0, ss->stream));
+        rc = launch_grad_fills(pb, ss->stream);
+        if (rc) return rc;
+        if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t1, ss->stream));
+        GSR_CUDA(cudaEventRecord(ss->join, ss->stream));
+    }
 
-    GSR_CUDA(cudaMemsetAsync(grad_rec, 0, (size_t)g.slots * GRAD_REC_FLOATS * sizeof(float), s));
+    // per-slot gradient records: only the live slots [256 b, 256 b + blk_count[b]) are read back, so only those are zeroed
+    // (58 MB instead of 288 MB at cfg3)
+    rc = launch_zero_grad_rec(g, grad_rec, s);
+    if (rc) return rc;
 
     RenderArgs ra;
     memset(&ra, 0, sizeof(ra));
@@ -644,7 +656,14 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     GSR_LAUNCHED(s, debug, "render_bwd");
     g_timer.mark(s, "render_bwd");
 
-    GSR_CUDA(cudaStreamWaitEvent(s, ss->join, 0)); // join
+    if (fills_on_side) {
+        GSR_CUDA(cudaStreamWaitEvent(s, ss->join, 0)); // join
+    } else {
+        if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t0, s));
+        rc = launch_grad_fills(pb, s);
+        if (rc) return rc;
+        if (g_timer.enabled) GSR_CUDA(cudaEventRecord(ss->t1, s));
+    }
     launch_preprocess_bwd(pb, s);
     GSR_LAUNCHED(s, debug, "preprocess_bwd");
     g_timer.mark(s, "preprocess_bwd");

@@ -3,84 +3,147 @@
 // Reference: duplicateWithKeys (rasterizer_impl.cu:70-111) emits R 64-bit (tile<<32 | depth) keys in Gaussian-id
 // order, CUB sorts them (rasterizer_impl.cu:307-312) and identifyTileRanges (rasterizer_impl.cu:116-138) finds
 // the per-tile ranges. Here:
-//   1. depth_keys      : (depth bits, slot) of the V visible Gaussians, in Gaussian-id order   [V pairs]
-//   2. radix sort      : stable on the 32 depth bits                                            [V pairs, gsr_scan_sort.cu]
-//   3. instance_offsets: exclusive scan of tiles_touched in depth order                         [V]
-//   4. emit            : one CTA per 2048 consecutive INSTANCES, one thread per instance (owner found by a warp 32-ary search
-//                        + a shared-memory binary search), so a Gaussian covering thousands of tiles costs the same per
-//                        instance as a small one                                                 [R pairs]
-//   5. radix sort      : stable on the tile id only (<= 16 bits)                                [R pairs]
+//   1. depth_keys      : (depth bits, slot) of the V visible Gaussians, in Gaussian-id order, + digit totals   [V pairs]
+//   2. radix sort      : stable on the 32 depth bits, one look-back kernel per pass                [V pairs, gsr_scan_sort.cu]
+//   3. instance_scan   : exclusive scan of tiles_touched in depth order (one look-back kernel) + chunk owners   [V]
+//   4. emit            : one CTA per 2048 consecutive INSTANCES, one thread per instance (owner range from the chunk table,
+//                        then a shared-memory binary search), so a Gaussian covering thousands of tiles costs the same per
+//                        instance as a small one; + digit totals of the tile sort              [R pairs]
+//   5. radix sort      : stable on the tile id only (<= 16 bits), one look-back kernel per pass    [R pairs]
 //   6. tile_ranges     : boundaries of the sorted tile ids                                      [R]
-// Stability of 2 and 5 gives exactly the reference's (tile, depth bits, Gaussian id) order.
+// 11 launches (round 1: 29). Stability of 2 and 5 gives exactly the reference's (tile, depth bits, Gaussian id) order.
 #include "gsr_common.cuh"
 
 namespace gsr
 {
 namespace
 {
-// (1) one CTA per slot-block; the visible slots of block b are [b*256, b*256 + blk_count[b]).
-__global__ void __launch_bounds__(PRE_BLOCK) depth_keys_kernel(GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+// (1) persistent CTAs stride over the slot-blocks; the visible slots of block b are [b*256, b*256 + blk_count[b]). Besides the
+// (depth bits, slot) pairs the kernel accumulates the digit totals of all four passes of the depth sort, so each pass is one kernel.
+__global__ void __launch_bounds__(PRE_BLOCK) depth_keys_kernel(GeomState g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                               uint32_t* __restrict__ hist)
 {
-    const uint32_t b = blockIdx.x;
-    const uint32_t cnt = g.blk_count[b];
-    if (threadIdx.x >= cnt) return;
-    const uint32_t slot = b * PRE_BLOCK + threadIdx.x;
-    const uint32_t dst = g.blk_offset[b] + threadIdx.x;
-    const float depth = g.rec[3 * (size_t)slot + 2].y;
-    keys[dst] = __float_as_uint(depth);
-    vals[dst] = slot;
+    __shared__ uint32_t s_h[4][256];
+#pragma unroll
+    for (int p = 0; p < 4; p++) s_h[p][threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t b = blockIdx.x; b < g.nblk; b += gridDim.x) {
+        const uint32_t cnt = g.blk_count[b];
+        if (threadIdx.x >= cnt) continue;
+        const uint32_t slot = b * PRE_BLOCK + threadIdx.x;
+        const uint32_t dst = g.blk_offset[b] + threadIdx.x;
+        const uint32_t key = __float_as_uint(g.rec[3 * (size_t)slot + 2].y);
+        keys[dst] = key;
+        vals[dst] = slot;
+#pragma unroll
+        for (int p = 0; p < 4; p++) atomicAdd(&s_h[p][(key >> (8 * p)) & 0xffu], 1u);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const uint32_t c = s_h[p][threadIdx.x];
+        if (c) atomicAdd(&hist[p * 256 + threadIdx.x], c);
+    }
 }
 
-// (3a) tiles_touched of the Gaussians in depth order
-__global__ void __launch_bounds__(256) sorted_tiles_kernel(const ushort4* __restrict__ rect, const uint32_t* __restrict__ sorted_slots, uint32_t V,
-                                                           uint32_t* __restrict__ out)
+// (3) tiles_touched of the Gaussians in depth order -> exclusive scan, in ONE kernel: CTA tiles of 2048 items handed out by an
+// atomic ticket, the running total passed from tile to tile through 64-bit look-back words (flag in the top two bits, like the
+// radix passes). While it holds item i's instance range [o_i, o_i + n_i) a thread also records, for every multiple of EMIT_CHUNK
+// inside it, that Gaussian i owns that instance: the emit kernel then starts from a table look-up instead of a search.
+constexpr int EMIT_CHUNK = 2048;
+constexpr unsigned long long SB_AGG = 1ull << 62, SB_INC = 2ull << 62, SB_VAL = (1ull << 62) - 1ull;
+
+__global__ void __launch_bounds__(256) instance_scan_kernel(const ushort4* __restrict__ rect, const uint32_t* __restrict__ sorted_slots, uint32_t V,
+                                                            uint32_t* __restrict__ soff, uint32_t* __restrict__ chunk_owner,
+                                                            unsigned long long* status /*[tiles] + ticket at [tiles]*/, uint32_t tiles)
 {
-    const uint32_t s = blockIdx.x * 256 + threadIdx.x;
-    if (s >= V) return;
-    const ushort4 r = rect[sorted_slots[s]];
-    out[s] = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(status + tiles, 1ull);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * SCAN_ITEMS + threadIdx.x * 8; // thread t owns 8 consecutive items
+    uint32_t v[8];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = 0;
+        if (base + k < V) {
+            const ushort4 r = rect[sorted_slots[base + k]];
+            v[k] = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
+        }
+        sum += v[k];
+    }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) wbase += c;
+        total += c;
+    }
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = status;
+        st[tile] = (tile == 0 ? SB_INC : SB_AGG) | (unsigned long long)total;
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            uint32_t t = tile - 1;
+            while (true) {
+                const unsigned long long w = st[t];
+                if ((w & ~SB_VAL) == 0ull) continue;
+                excl += w & SB_VAL;
+                if (w & SB_INC) break;
+                t--;
+            }
+            st[tile] = SB_INC | (excl + total);
+        }
+        s_prefix = excl;
+    }
+    __syncthreads();
+    uint32_t o = (uint32_t)s_prefix + wbase + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (base + k < V) {
+            soff[base + k] = o;
+            const uint32_t e = o + v[k];
+            for (uint32_t c = (o + EMIT_CHUNK - 1) / EMIT_CHUNK; c * EMIT_CHUNK < e; c++) chunk_owner[c] = base + k;
+            if (base + k == V - 1) soff[V] = e;
+            o = e;
+        }
+    }
 }
 
 // (4) One CTA per chunk of EMIT_CHUNK consecutive INSTANCES (not Gaussians): the near-camera Gaussians of a scene cover
 // thousands of tiles each, so a per-Gaussian (or per-256-Gaussian) decomposition leaves a few CTAs with nearly all the work.
-// The CTA finds the owners of its first and last instance with a 32-ary warp search of the offset array, stages the owners'
-// offsets / rectangles / slots in shared memory and resolves every instance with a shared-memory binary search.
-constexpr int EMIT_CHUNK = 2048;
-
-// largest j in [0, n) with a[j] <= key, for non-decreasing a with a[0] <= key; whole warp cooperates (32-ary steps)
-__device__ __forceinline__ uint32_t warp_upper_owner(const uint32_t* __restrict__ a, uint32_t n, uint32_t key, uint32_t lane)
-{
-    uint32_t lo = 0, len = n; // answer in [lo, lo+len)
-    while (len > 1) {
-        const uint32_t step = (len + 31) / 32;
-        const uint32_t idx = lo + lane * step;
-        const bool le = idx < lo + len && a[idx] <= key;
-        const uint32_t m = __ballot_sync(0xffffffffu, le);
-        const uint32_t k = 31 - __clz(m); // lane 0 always satisfies a[lo] <= key
-        lo = lo + k * step;
-        len = min(step, n - lo);
-    }
-    return lo;
-}
-
+// The owners of the chunk's first and last instance come from chunk_owner (written by the scan); the CTA stages the owners'
+// offsets / rectangles / slots in shared memory and resolves every instance with a shared-memory binary search. It also
+// accumulates the digit totals of the tile sort's passes, so that each of them is one kernel.
 __global__ void __launch_bounds__(256) emit_kernel(const ushort4* __restrict__ rect, const uint32_t* __restrict__ sorted_slots,
-                                                   const uint32_t* __restrict__ soff, uint32_t V, uint32_t R, int grid_x,
+                                                   const uint32_t* __restrict__ soff, const uint32_t* __restrict__ chunk_owner, uint32_t V,
+                                                   uint32_t R, int grid_x, int digit_bits, int passes, uint32_t* __restrict__ hist,
                                                    uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals)
 {
-    __shared__ uint32_t s_off[EMIT_CHUNK + 2];
-    __shared__ ushort4 s_rect[EMIT_CHUNK + 1];
-    __shared__ uint32_t s_slot[EMIT_CHUNK + 1];
-    __shared__ uint32_t s_owner[2];
+    __shared__ uint32_t s_off[EMIT_CHUNK + 4];
+    __shared__ ushort4 s_rect[EMIT_CHUNK + 2];
+    __shared__ uint32_t s_slot[EMIT_CHUNK + 2];
+    __shared__ uint32_t s_h[4][256];
+#pragma unroll
+    for (int p = 0; p < 4; p++) s_h[p][threadIdx.x] = 0;
     const uint32_t begin = blockIdx.x * EMIT_CHUNK;
     const uint32_t end = min(R, begin + EMIT_CHUNK);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (warp < 2) {
-        const uint32_t j = warp_upper_owner(soff, V, warp == 0 ? begin : end - 1, lane);
-        if (lane == 0) s_owner[warp] = j;
-    }
-    __syncthreads();
-    // every visible Gaussian owns >= 1 instance, so at most EMIT_CHUNK owners overlap the chunk
-    const uint32_t j0 = s_owner[0], cnt = s_owner[1] - j0 + 1;
+    // every visible Gaussian owns >= 1 instance, so at most EMIT_CHUNK owners overlap the chunk (+ 1: j1 may be the next chunk's first owner)
+    const uint32_t j0 = chunk_owner[blockIdx.x];
+    const uint32_t j1 = (blockIdx.x + 1u) * EMIT_CHUNK < R ? chunk_owner[blockIdx.x + 1] : V - 1;
+    const uint32_t cnt = j1 - j0 + 1;
     for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
         const uint32_t slot = sorted_slots[j0 + i];
         s_slot[i] = slot;
@@ -89,6 +152,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const ushort4* __restrict__ r
     }
     if (threadIdx.x == 0) s_off[cnt] = soff[j0 + cnt];
     __syncthreads();
+    const uint32_t mask = (1u << digit_bits) - 1u;
     for (uint32_t k = begin + threadIdx.x; k < end; k += 256) {
         uint32_t lo = 0, hi = cnt; // largest j in [0,cnt) with s_off[j] <= k
         while (hi - lo > 1) {
@@ -101,51 +165,74 @@ __global__ void __launch_bounds__(256) emit_kernel(const ushort4* __restrict__ r
         const uint32_t w = (uint32_t)(r.z - r.x);
         const uint32_t ty = r.y + local / w;
         const uint32_t tx = r.x + local % w;
-        out_keys[k] = ty * (uint32_t)grid_x + tx;
+        const uint32_t key = ty * (uint32_t)grid_x + tx;
+        out_keys[k] = key;
         out_vals[k] = s_slot[lo];
+        for (int p = 0; p < passes; p++) atomicAdd(&s_h[p][(key >> (p * digit_bits)) & mask], 1u);
+    }
+    __syncthreads();
+    for (int p = 0; p < passes; p++) {
+        const uint32_t c = s_h[p][threadIdx.x];
+        if (c) atomicAdd(&hist[p * 256 + threadIdx.x], c);
     }
 }
 
-// (6) boundaries of the sorted tile ids; ranges was zeroed, so untouched tiles stay (0,0) like the reference.
+// (6) boundaries of the sorted tile ids, four keys per thread; ranges was zeroed, so untouched tiles stay (0,0) like the reference.
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tkeys, uint32_t R, uint2* __restrict__ ranges)
 {
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t cur = tkeys[i];
-    if (i == 0) ranges[cur].x = 0;
-    else {
-        const uint32_t prev = tkeys[i - 1];
-        if (cur != prev) {
+    const uint32_t i0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= R) return;
+    uint32_t k[4];
+    if (i0 + 3 < R) {
+        const uint4 q = *reinterpret_cast<const uint4*>(tkeys + i0); // the key buffers are 256-byte aligned
+        k[0] = q.x; k[1] = q.y; k[2] = q.z; k[3] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) k[j] = i0 + j < R ? tkeys[i0 + j] : 0u;
+    }
+    uint32_t prev = i0 ? tkeys[i0 - 1] : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i = i0 + j;
+        if (i >= R) break;
+        const uint32_t cur = k[j];
+        if (i == 0) ranges[cur].x = 0;
+        else if (cur != prev) {
             ranges[prev].y = i;
             ranges[cur].x = i;
         }
+        if (i == R - 1) ranges[cur].y = R;
+        prev = cur;
     }
-    if (i == R - 1) ranges[cur].y = R;
 }
 } // namespace
 
-int launch_depth_keys(const GeomState& g, cudaStream_t s)
+int launch_depth_keys(const GeomState& g, uint32_t* hist, cudaStream_t s)
 {
     if (g.nblk == 0) return 0;
-    depth_keys_kernel<<<g.nblk, PRE_BLOCK, 0, s>>>(g, g.dkeys[0], g.dvals[0]); count_launches(1);
+    const uint32_t grid = g.nblk < 148u * 8u ? g.nblk : 148u * 8u;
+    depth_keys_kernel<<<grid, PRE_BLOCK, 0, s>>>(g, g.dkeys[0], g.dvals[0], hist); count_launches(1);
     return 0;
 }
 
-int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, const uint32_t* sorted_slots, cudaStream_t s)
+int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, cudaStream_t s)
 {
+    (void)R;
     if (V == 0) {
         GSR_CUDA(cudaMemsetAsync(b.soff, 0, sizeof(uint32_t), s));
         return 0;
     }
-    sorted_tiles_kernel<<<(V + 255) / 256, 256, 0, s>>>(g.rect, sorted_slots, V, b.soff); count_launches(1);
-    return exclusive_scan_u32(b.soff, b.soff, V, true, b.scan_part, s);
+    const uint32_t tiles = (V + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    instance_scan_kernel<<<tiles, 256, 0, s>>>(g.rect, sorted_slots, V, b.soff, b.chunk_owner, b.scan_status, tiles); count_launches(1);
+    return 0;
 }
 
-int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, int grid_x,
-                uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s)
+int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, int grid_x, int digit_bits, int passes,
+                uint32_t* hist, uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s)
 {
     if (V == 0 || R == 0) return 0;
-    emit_kernel<<<(R + EMIT_CHUNK - 1) / EMIT_CHUNK, 256, 0, s>>>(g.rect, sorted_slots, b.soff, V, R, grid_x, out_keys, out_vals);
+    emit_kernel<<<(R + EMIT_CHUNK - 1) / EMIT_CHUNK, 256, 0, s>>>(g.rect, sorted_slots, b.soff, b.chunk_owner, V, R, grid_x, digit_bits, passes, hist,
+                                                                   out_keys, out_vals);
     count_launches(1);
     return 0;
 }
@@ -154,7 +241,7 @@ int launch_tile_ranges(const uint32_t* sorted_tile_keys, uint32_t R, uint2* rang
 {
     GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), s));
     if (R == 0) return 0;
-    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(sorted_tile_keys, R, ranges); count_launches(1);
+    tile_ranges_kernel<<<(R + 1023) / 1024, 256, 0, s>>>(sorted_tile_keys, R, ranges); count_launches(1);
     return 0;
 }
 } // namespace gsr

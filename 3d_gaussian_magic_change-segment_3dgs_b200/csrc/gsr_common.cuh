@@ -48,9 +48,12 @@ struct BinState
     uint32_t* vals_alt;   // [R]
     uint32_t* tkeys[2];   // [R] tile ids (ping-pong)
     uint32_t* soff;       // [V+1] exclusive scan of tiles_touched in depth order
-    uint32_t* hist;       // radix block histograms followed by their scan partials
+    uint32_t* hist;       // tile sort workspace: [passes][256] digit totals | 32 tickets | [passes][tiles][256] look-back words
     size_t hist_words;
-    uint32_t* scan_part;  // partials of the instance-offset scan
+    unsigned long long* scan_status; // look-back words of the instance-offset scan, one per 2048 Gaussians (+ its ticket)
+    size_t scan_status_words;
+    uint32_t* chunk_owner; // [chunks + 1]: depth-order index of the Gaussian that owns instance 2048 * c
+    size_t zero_bytes;     // everything from `hist` on is zeroed by one memset before the binning kernels
 };
 
 struct ImgState
@@ -88,14 +91,14 @@ inline size_t geom_layout(char* base, int P, GeomState& g)
         carve(p, g.dkeys[i], (size_t)g.slots);
         carve(p, g.dvals[i], (size_t)g.slots);
     }
+    // depth sort (32 bits = 4 passes, one kernel each): [4][256] digit totals | 32 tickets | [4][tiles][256] look-back words
     const size_t nb = ((size_t)g.slots + RADIX_ITEMS - 1) / RADIX_ITEMS;
-    const size_t h = 256 * (nb + 1);
-    g.dhist_words = h + (h + SCAN_ITEMS - 1) / SCAN_ITEMS + 64;
+    g.dhist_words = 4 * 256 + 32 + 4 * nb * 256;
     carve(p, g.dhist, g.dhist_words);
     return (size_t)(p - base) + 256;
 }
 
-inline size_t bin_layout(char* base, size_t V, size_t R, BinState& b)
+inline size_t bin_layout(char* base, size_t V, size_t R, int tile_bits, BinState& b)
 {
     char* p = base;
     carve(p, b.point_list, R);
@@ -103,12 +106,15 @@ inline size_t bin_layout(char* base, size_t V, size_t R, BinState& b)
     carve(p, b.tkeys[0], R);
     carve(p, b.tkeys[1], R);
     carve(p, b.soff, V + 1);
-    size_t n = R > V ? R : V;
-    size_t nb = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
-    size_t h = 256 * (nb + 1);
-    b.hist_words = h + (h + SCAN_ITEMS - 1) / SCAN_ITEMS + 64;
+    const size_t nb = (R + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    const size_t passes = (size_t)((tile_bits + 7) / 8);
+    b.hist_words = passes * 256 + 32 + passes * nb * 256;
     carve(p, b.hist, b.hist_words);
-    carve(p, b.scan_part, (V + SCAN_ITEMS) / SCAN_ITEMS + 64);
+    char* zero_from = (char*)b.hist;
+    b.scan_status_words = (V + SCAN_ITEMS - 1) / SCAN_ITEMS + 8;
+    carve(p, b.scan_status, b.scan_status_words);
+    b.zero_bytes = (size_t)(p - zero_from);
+    carve(p, b.chunk_owner, nb + 2);
     return (size_t)(p - base) + 256;
 }
 
@@ -264,11 +270,15 @@ struct RenderArgs
 int launch_preprocess_fwd(const PreFwdArgs& a, cudaStream_t s);
 int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s);
 int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s);
+int launch_zero_grad_rec(const GeomState& g, float* grad_rec, cudaStream_t s);
 int launch_block_offsets(const GeomState& g, cudaStream_t s);
-int launch_depth_keys(const GeomState& g, cudaStream_t s);
-int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, const uint32_t* sorted_slots, cudaStream_t s);
-int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, int grid_x,
-                uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s);
+// depth (key, slot) pairs of the visible Gaussians + the digit totals of the four depth-sort passes (hist: [4][256], zeroed)
+int launch_depth_keys(const GeomState& g, uint32_t* hist, cudaStream_t s);
+// tiles_touched in depth order -> exclusive scan (soff[0..V]) + owner of every 2048th instance, one kernel (b.scan_status zeroed)
+int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, cudaStream_t s);
+// (tile id, slot) per instance in depth order + digit totals of the tile sort's passes (hist: [passes][256], zeroed)
+int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, int grid_x, int digit_bits, int passes,
+                uint32_t* hist, uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s);
 int launch_tile_ranges(const uint32_t* sorted_tile_keys, uint32_t R, uint2* ranges, uint32_t T, cudaStream_t s);
 int launch_render_fwd(const RenderArgs& a, int S, cudaStream_t s);
 int launch_render_bwd(const RenderArgs& a, int S, cudaStream_t s);
@@ -281,6 +291,11 @@ int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, bool write
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* hist, size_t hist_words, cudaStream_t s,
                      const uint32_t* n_dev = nullptr);
 int radix_num_passes(int nbits);
+int radix_digit_bits(int nbits);
+size_t radix_lookback_ws_words(uint32_t n_cap, int nbits);
+// one kernel per pass (decoupled look-back); see gsr_scan_sort.cu
+int radix_sort_pairs_lookback(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* ws, size_t ws_words, bool hist_ready,
+                              cudaStream_t s, const uint32_t* n_dev = nullptr);
 
 int knn_run(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t knn_workspace_bytes(int P);

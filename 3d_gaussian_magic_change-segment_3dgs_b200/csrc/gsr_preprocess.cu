@@ -781,6 +781,16 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
     } // groups
 }
 
+// Zero the gradient records of the live slots only: one warp per slot-block, 3 x 16 bytes per visible Gaussian, contiguous.
+__global__ void __launch_bounds__(256) zero_grad_rec_kernel(GeomState g, float4* __restrict__ grad_rec)
+{
+    const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= g.nblk) return;
+    const uint32_t n4 = g.blk_count[b] * (GRAD_REC_FLOATS / 4);
+    float4* dst = grad_rec + (size_t)b * PRE_BLOCK * (GRAD_REC_FLOATS / 4);
+    for (uint32_t i = threadIdx.x & 31u; i < n4; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
                                                            uint8_t* __restrict__ present)
 {
@@ -831,6 +841,13 @@ int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
         for (auto& f : fills)
             if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
     }
+    return 0;
+}
+
+int launch_zero_grad_rec(const GeomState& g, float* grad_rec, cudaStream_t s)
+{
+    if (g.nblk == 0) return 0;
+    zero_grad_rec_kernel<<<(g.nblk + 7) / 8, 256, 0, s>>>(g, reinterpret_cast<float4*>(grad_rec)); count_launches(1);
     return 0;
 }
 

@@ -314,6 +314,170 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_sort_coop_kernel(const Ra
         cur ^= 1;
     }
 }
+
+// ------------------------------------------------------------------------------------------ single-kernel passes (decoupled look-back)
+// One kernel per radix pass instead of histogram + 2-kernel scan + scatter. The digit totals of ALL passes are known before the
+// first pass (accumulated by the kernel that produces the keys, or by digit_hist_all_kernel), so a pass only needs, per CTA tile
+// and digit, the number of keys with that digit in the tiles before it. Tile t publishes its own count (flag AGGREGATE) as soon as
+// it has counted, walks back over its predecessors' published words until it meets an INCLUSIVE one, and publishes its own
+// inclusive prefix. Tiles are handed out by an atomic ticket, so every predecessor of a running tile is running or done and the
+// walk cannot dead-lock. Ranking inside the tile is the stable match.any scheme of tile_scatter_body.
+constexpr uint32_t LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_VAL = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+struct LookbackPassArgs
+{
+    const uint32_t* keys_in;
+    const uint32_t* vals_in;
+    uint32_t* keys_out;
+    uint32_t* vals_out;
+    uint32_t n;
+    const uint32_t* n_dev;
+    int shift;
+    uint32_t mask;
+    const uint32_t* digit_total; // [256] keys per digit of this pass (whole input)
+    uint32_t* status;            // [tiles][256], zeroed
+    uint32_t* ticket;            // zeroed
+};
+
+__global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(const LookbackPassArgs a)
+{
+    __shared__ uint32_t s_cnt[8][256];
+    __shared__ uint32_t s_gbase[256];
+    __shared__ uint32_t s_keys[RADIX_ITEMS];
+    __shared__ uint32_t s_vals[RADIX_ITEMS];
+    __shared__ uint32_t s_warp[8], s_warp2[8];
+    __shared__ uint32_t s_tile;
+    const uint32_t n = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    for (uint32_t i = threadIdx.x; i < 8 * 256; i += RADIX_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tile_base = tile * RADIX_ITEMS;
+    if (tile_base >= n) return;
+    const uint32_t tile_n = min((uint32_t)RADIX_ITEMS, n - tile_base);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int shift = a.shift;
+    const uint32_t mask = a.mask;
+
+    const uint32_t wbase = tile_base + warp * RADIX_WARP_ITEMS;
+    uint32_t key[RADIX_PER_THREAD], val[RADIX_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+        const uint32_t i = wbase + k * 32 + lane;
+        key[k] = i < n ? a.keys_in[i] : 0xffffffffu;
+        val[k] = i < n ? a.vals_in[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+        const uint32_t i = wbase + k * 32 + lane;
+        if (i < n) atomicAdd(&s_cnt[warp][(key[k] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    const bool has_digit = threadIdx.x <= mask;
+    uint32_t tot = 0, wpre[8];
+    if (has_digit) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            wpre[w] = tot;
+            tot += s_cnt[w][threadIdx.x];
+        }
+        st_volatile_u32(a.status + (size_t)tile * 256 + threadIdx.x, (tile == 0 ? LB_INC : LB_AGG) | tot); // publish early
+    }
+    // two block-wide exclusive scans over the digits: this tile's counts (position of the digit run inside the tile) and the
+    // global digit totals (start of the digit's region in the output)
+    const uint32_t gtot = has_digit ? a.digit_total[threadIdx.x] : 0u;
+    uint32_t incl = tot, gincl = gtot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o), g = __shfl_up_sync(0xffffffffu, gincl, o);
+        if (lane >= (uint32_t)o) {
+            incl += v;
+            gincl += g;
+        }
+    }
+    if (lane == 31) {
+        s_warp[warp] = incl;
+        s_warp2[warp] = gincl;
+    }
+    __syncthreads();
+    uint32_t dstart = incl - tot, gstart = gincl - gtot;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++)
+        if (w < warp) {
+            dstart += s_warp[w];
+            gstart += s_warp2[w];
+        }
+    if (has_digit) {
+        uint32_t excl = 0;
+        if (tile > 0) {
+            uint32_t t = tile - 1;
+            while (true) {
+                const uint32_t v = ld_volatile_u32(a.status + (size_t)t * 256 + threadIdx.x);
+                if ((v & ~LB_VAL) == 0u) continue; // not published yet
+                excl += v & LB_VAL;
+                if (v & LB_INC) break;
+                t--; // tile 0 always publishes INCLUSIVE, so t never passes 0
+            }
+            st_volatile_u32(a.status + (size_t)tile * 256 + threadIdx.x, LB_INC | (excl + tot));
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++) s_cnt[w][threadIdx.x] = dstart + wpre[w]; // rank base inside the tile
+        s_gbase[threadIdx.x] = gstart + excl - dstart;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+        const uint32_t i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0x100u + lane;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t pos = 0;
+        if (valid) pos = s_cnt[warp][d] + rank;
+        __syncwarp();
+        if (valid && rank == 0) s_cnt[warp][d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            s_keys[pos] = key[k];
+            s_vals[pos] = val[k];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tile_n; i += RADIX_THREADS) {
+        const uint32_t kk = s_keys[i];
+        const uint32_t g = s_gbase[(kk >> shift) & mask] + i;
+        a.keys_out[g] = kk;
+        a.vals_out[g] = s_vals[i];
+    }
+}
+
+// digit totals of every pass in one read of the keys (for callers whose key producer does not accumulate them itself)
+__global__ void __launch_bounds__(RADIX_THREADS) digit_hist_all_kernel(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* n_dev,
+                                                                      int passes, int digit_bits, uint32_t* hist /*[passes][256]*/)
+{
+    __shared__ uint32_t s_h[4][256];
+    if (n_dev) n = min(*n_dev, n);
+    for (int p = 0; p < passes; p++) s_h[p][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t mask = (1u << digit_bits) - 1u;
+    for (uint32_t i = blockIdx.x * RADIX_THREADS + threadIdx.x; i < n; i += gridDim.x * RADIX_THREADS) {
+        const uint32_t k = keys[i];
+        for (int p = 0; p < passes; p++) atomicAdd(&s_h[p][(k >> (p * digit_bits)) & mask], 1u);
+    }
+    __syncthreads();
+    for (int p = 0; p < passes; p++) {
+        const uint32_t c = s_h[p][threadIdx.x];
+        if (c) atomicAdd(&hist[p * 256 + threadIdx.x], c);
+    }
+}
 } // namespace
 
 int exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, bool write_total, uint32_t* partials, cudaStream_t s)
@@ -382,6 +546,58 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits
         if (rc) return rc;
         radix_scatter_kernel<<<nb, RADIX_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, n_dev, shift, mask, nb, hist);
         count_launches(1);
+        cur ^= 1;
+    }
+    return cur;
+}
+} // namespace gsr
+
+namespace gsr
+{
+size_t radix_lookback_ws_words(uint32_t n_cap, int nbits)
+{
+    const int passes = radix_num_passes(nbits);
+    const size_t tiles = ((size_t)n_cap + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    return (size_t)passes * 256 + 32 + (size_t)passes * tiles * 256;
+}
+
+int radix_digit_bits(int nbits)
+{
+    const int passes = radix_num_passes(nbits);
+    return passes ? (nbits + passes - 1) / passes : 0;
+}
+
+// Stable LSD radix sort, ONE kernel per pass. ws: radix_lookback_ws_words(n, nbits) words laid out as
+// [passes][256] digit totals | 32 tickets | [passes][tiles][256] look-back words. With hist_ready the caller has zeroed the
+// whole workspace and its key producer has accumulated the digit totals (digit p = bits [p * digit_bits, (p + 1) * digit_bits));
+// otherwise the workspace is zeroed and the totals are computed here. n < 2^30 (the look-back words carry 30 bits).
+int radix_sort_pairs_lookback(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* ws, size_t ws_words, bool hist_ready,
+                              cudaStream_t s, const uint32_t* n_dev)
+{
+    const int passes = radix_num_passes(nbits);
+    if (n == 0 || passes == 0) return 0;
+    if (n >= (1u << 30) || passes > 4) return radix_sort_pairs(keys, vals, n, nbits, ws, ws_words, s, n_dev); // multi-kernel path
+    if (radix_lookback_ws_words(n, nbits) > ws_words) {
+        set_error("radix_sort_pairs_lookback: workspace too small (%zu > %zu words)", radix_lookback_ws_words(n, nbits), ws_words);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    const int digit_bits = radix_digit_bits(nbits);
+    const uint32_t tiles = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    uint32_t* hist = ws;
+    uint32_t* tickets = ws + (size_t)passes * 256;
+    uint32_t* status = tickets + 32;
+    if (!hist_ready) {
+        GSR_CUDA(cudaMemsetAsync(ws, 0, radix_lookback_ws_words(n, nbits) * sizeof(uint32_t), s));
+        const uint32_t grid = tiles < 1184u ? tiles : 1184u;
+        digit_hist_all_kernel<<<grid, RADIX_THREADS, 0, s>>>(keys[0], n, n_dev, passes, digit_bits, hist); count_launches(1);
+    }
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+        LookbackPassArgs a;
+        a.keys_in = keys[cur]; a.vals_in = vals[cur]; a.keys_out = keys[cur ^ 1]; a.vals_out = vals[cur ^ 1];
+        a.n = n; a.n_dev = n_dev; a.shift = p * digit_bits; a.mask = (1u << digit_bits) - 1u;
+        a.digit_total = hist + p * 256; a.status = status + (size_t)p * tiles * 256; a.ticket = tickets + p;
+        radix_lookback_pass_kernel<<<tiles, RADIX_THREADS, 0, s>>>(a); count_launches(1);
         cur ^= 1;
     }
     return cur;

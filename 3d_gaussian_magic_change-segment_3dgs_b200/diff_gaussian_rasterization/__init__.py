@@ -194,7 +194,7 @@ def _forward_native(means3D, sh, colors_precomp, segments, opacities, scales, ro
             alloc.release()  # the ctypes callback <-> bound method cycle would otherwise pin ~1 GB of state until a GC pass
         _lib.check(rc, "gsr_forward")
         e = lambda t: t if t is not None else torch.empty(0, dtype=torch.uint8, device=device)
-        return R.value, color, depth, segment, alpha, radii, e(bufs[0]), e(bufs[1]), e(bufs[2])
+        return NumRendered(R.value, L.gsr_last_num_visible()), color, depth, segment, alpha, radii, e(bufs[0]), e(bufs[1]), e(bufs[2])
 
 
 def _forward_parts_native(parts, rs):
@@ -247,7 +247,7 @@ def _forward_parts_native(parts, rs):
             alloc.release()
         _lib.check(rc, "gsr_forward")
         e = lambda t: t if t is not None else torch.empty(0, dtype=torch.uint8, device=device)
-        return R.value, color, depth, segment, alpha, radii, e(bufs[0]), e(bufs[1]), e(bufs[2])
+        return NumRendered(R.value, L.gsr_last_num_visible()), color, depth, segment, alpha, radii, e(bufs[0]), e(bufs[1]), e(bufs[2])
 
 
 def count_work(P, W, H, geomBuffer, binningBuffer, imgBuffer, num_rendered):

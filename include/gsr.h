@@ -235,6 +235,17 @@ size_t gsr_image_loss_scratch_bytes(int32_t C, int32_t H, int32_t W);
 int gsr_image_loss(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, float lambda_dssim, float grad_scale,
                    float* loss_out, float* dL_dimage, void* scratch, size_t scratch_bytes, gsr_stream_t stream);
 
+/* Depth supervision of the training step (train.py:118-121 with depth_loss_choice 'localrf',
+ * utils/loss_utils.py:88-102 compute_depth_loss, and the normalisation of gaussian_renderer/__init__.py:375):
+ *   mode 0: in = compute_depth_loss's dyn_depth x;   mode 1: in = the rasterizer's raw depth d, and x = 1 / max(d / (max(d) + 1e-5), 1e-6)
+ *   t = median(x) (lower middle element), s = mean|x - t|, same for gt;  a = ((x - t)/s - (gt - tg)/sg)^2;
+ *   loss = lambda * mean(a where a <= quantile(a, 0.8) else 0)            (quantile with torch's float32 rank and lerp)
+ * loss_out[1] (device). grad_out [n] = grad_scale * dloss/d(in) (NULL: value only), including the paths through the median element,
+ * the mean absolute deviation and (mode 1) the arg-max pixel. Order statistics by radix select, no sort, no host sync; n < 2^31. */
+size_t gsr_depth_loss_scratch_bytes(int64_t n);
+int gsr_depth_loss(const float* in, const float* gt, int64_t n, float lambda, float grad_scale, int32_t mode, float* loss_out, float* grad_out,
+                   void* scratch, size_t scratch_bytes, gsr_stream_t stream);
+
 /* Densify / prune as one index list (replaces the per-tensor boolean masks and torch.cat of
  * scene/gaussian_model.py:377-441 over seven parameters and their two Adam moments). src and dst are flat buffers of
  * num_blocks blocks; block k starts at float src_offsets[k] (resp. dst_offsets[k]) and holds n_src (resp. n_out) rows of

@@ -276,7 +276,7 @@ def test_packet_capacity_comes_from_the_forward_it_belongs_to():
     mv = importlib.import_module(H.PKG_NAME + ".multiview")
     syn = H.synthetic()
     gs = H.to_dev(syn.make_gaussians(40_000, 21))
-    cam_a, cam_b = syn.make_camera(160, 120), syn.make_camera(160, 120, yaw_deg=90.0, radius=40.0)  # b: far away, few visible
+    cam_a, cam_b = syn.make_camera(160, 120, yaw_deg=90.0, radius=40.0), syn.make_camera(160, 120)  # a: far away, sees everything
     rs_a, rs_b = H.settings(cam_a, torch.zeros(3)), H.settings(cam_b, torch.zeros(3))
     ug = H.to_dev(syn.upstream_grads(160, 120, 5))
     fwd_a = mv.native_view_forward(D, gs, rs_a)

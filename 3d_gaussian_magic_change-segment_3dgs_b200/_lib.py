@@ -76,10 +76,10 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 # every symbol include/gsr.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
-           "gsr_backward_packets", "gsr_apply_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
+           "gsr_backward_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
            "gsr_peer_free", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible", "gsr_microbench", "gsr_count_work", "gsr_depth_loss", "gsr_depth_loss_scratch_bytes"]
 GSR_ABI_VERSION = 3  # include/gsr.h
-GSR_PACKET_WORDS = 17
+GSR_PACKET_WORDS = 16
 GSR_PEER_HANDLE_BYTES = 64
 GSR_MAX_GATHER_VIEWS = 64
 
@@ -148,9 +148,6 @@ def lib():
                                 ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int32, ctypes.c_void_p]
     L.gsr_packet_index_words.restype = ctypes.c_size_t
     L.gsr_packet_index_words.argtypes = [ctypes.c_int32]
-    L.gsr_apply_packets.restype = ctypes.c_int
-    L.gsr_apply_packets.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
-                                    ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.POINTER(GsrParamGrads), ctypes.c_void_p]
     L.gsr_last_num_visible.restype = ctypes.c_uint32
     L.gsr_mark_visible.restype = ctypes.c_int
     L.gsr_mark_visible.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]

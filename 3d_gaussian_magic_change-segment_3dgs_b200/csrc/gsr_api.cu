@@ -461,27 +461,6 @@ extern "C" int gsr_backward_packets(const GsrView* view, const GsrGaussians* in,
                          vis_index);
 }
 
-extern "C" int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, const float* campos,
-                                 const uint32_t* packets, uint32_t capacity, const uint32_t* count_dev, const GsrParamGrads* grads,
-                                 gsr_stream_t stream_)
-{
-    if (P <= 0 || capacity == 0) return 0;
-    if (!means3D || !campos || !packets || !count_dev || !grads || sh_coeffs > 16 || sh_degree < 0 || sh_degree > 3) {
-        set_error("gsr_apply_packets: invalid argument");
-        return GSR_ERR_INVALID_ARGUMENT;
-    }
-    if (grads->dL_dsh_rest) {
-        set_error("gsr_apply_packets: split SH outputs (dL_dsh_rest) are only built in gsr_gather_packets");
-        return GSR_ERR_UNSUPPORTED;
-    }
-    ApplyPacketsArgs a;
-    a.P = P; a.D = sh_degree; a.M = sh_coeffs; a.S = num_class; a.means3D = means3D; a.campos = campos;
-    a.packets = packets; a.capacity = capacity; a.count = count_dev; a.out = *grads;
-    launch_apply_packets(a, (cudaStream_t)stream_);
-    GSR_LAUNCHED((cudaStream_t)stream_, false, "apply_packets");
-    return 0;
-}
-
 extern "C" size_t gsr_packet_index_words(int32_t P) { return P > 0 ? (2 * (size_t)((P + 31) / 32) + 31) / 32 * 32 : 0; }
 
 extern "C" int gsr_gather_packets_v(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D,

@@ -65,6 +65,8 @@ struct ImgState
 constexpr int RADIX_ITEMS = 2048;  // keys per radix CTA (256 threads x 8)
 constexpr int SCAN_ITEMS = 2048;   // items per scan CTA (256 threads x 8)
 
+size_t radix_lookback_ws_words(uint32_t n_cap, int nbits); // gsr_scan_sort.cu
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <typename T>
@@ -92,8 +94,7 @@ inline size_t geom_layout(char* base, int P, GeomState& g)
         carve(p, g.dvals[i], (size_t)g.slots);
     }
     // depth sort (32 bits = 4 passes, one kernel each): [4][256] digit totals | 32 tickets | [4][tiles][256] look-back words
-    const size_t nb = ((size_t)g.slots + RADIX_ITEMS - 1) / RADIX_ITEMS;
-    g.dhist_words = 4 * 256 + 32 + 4 * nb * 256;
+    g.dhist_words = radix_lookback_ws_words(g.slots, 32);
     carve(p, g.dhist, g.dhist_words);
     return (size_t)(p - base) + 256;
 }
@@ -107,8 +108,7 @@ inline size_t bin_layout(char* base, size_t V, size_t R, int tile_bits, BinState
     carve(p, b.tkeys[1], R);
     carve(p, b.soff, V + 1);
     const size_t nb = (R + RADIX_ITEMS - 1) / RADIX_ITEMS;
-    const size_t passes = (size_t)((tile_bits + 7) / 8);
-    b.hist_words = passes * 256 + 32 + passes * nb * 256;
+    b.hist_words = radix_lookback_ws_words((uint32_t)R, tile_bits);
     carve(p, b.hist, b.hist_words);
     char* zero_from = (char*)b.hist;
     b.scan_status_words = (V + SCAN_ITEMS - 1) / SCAN_ITEMS + 8;
@@ -231,18 +231,6 @@ struct GatherPacketsArgs
     GsrParamGrads out;
 };
 int launch_gather_packets(const GatherPacketsArgs& a, cudaStream_t s);
-
-struct ApplyPacketsArgs
-{
-    int P, D, M, S;
-    const float* means3D;
-    const float* campos;
-    const uint32_t* packets;
-    uint32_t capacity;
-    const uint32_t* count;
-    GsrParamGrads out;
-};
-int launch_apply_packets(const ApplyPacketsArgs& a, cudaStream_t s);
 
 struct RenderArgs
 {

@@ -376,7 +376,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdArgs& a, const bo
     // ---- SH gradient rows: each 192-B row leaves the warp as whole 128-B + 64-B bursts (a per-thread row write would
     //      touch 32 different rows per store instruction, half a sector each) ----
     if (a.packets) {
-        // ---- packet mode: 17 words per visible Gaussian; the receiver rebuilds the SH rows from the colour gradient ----
+        // ---- packet mode: 16 words per visible Gaussian; the receiver rebuilds the SH rows from the colour gradient ----
         if (visible && r < a.packet_capacity) {
             float3 dRGB = dL_dcolor;
             if (a.shs != nullptr) { // the clamp mask of sh_backward (backward.cu:31-34)
@@ -385,19 +385,15 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdArgs& a, const bo
                 dRGB.y *= (cb & 2u) ? 0 : 1;
                 dRGB.z *= (cb & 4u) ? 0 : 1;
             }
-            uint32_t* pk = a.packets + (size_t)r * GSR_PACKET_WORDS;
             if (a.vis_index) { // order-independent atomics: the index is deterministic
                 atomicOr(&a.vis_index[2 * ((uint32_t)idx >> 5)], 1u << (idx & 31));
                 atomicMax(&a.vis_index[2 * ((uint32_t)idx >> 5) + 1], ~r); // ~(smallest packet index of the group)
             }
-            pk[0] = (uint32_t)idx;
-            float* pf = reinterpret_cast<float*>(pk);
-            pf[1] = dRGB.x; pf[2] = dRGB.y; pf[3] = dRGB.z;
-            pf[4] = dL_dmean.x; pf[5] = dL_dmean.y; pf[6] = dL_dmean.z;
-            pf[7] = dL_dopacity;
-            pf[8] = dL_dseg.x; pf[9] = dL_dseg.y;
-            pf[10] = dL_dscale.x; pf[11] = dL_dscale.y; pf[12] = dL_dscale.z;
-            pf[13] = dL_drot.x; pf[14] = dL_drot.y; pf[15] = dL_drot.z; pf[16] = dL_drot.w;
+            float4* pk = reinterpret_cast<float4*>(a.packets + (size_t)r * GSR_PACKET_WORDS); // 64-byte aligned
+            pk[0] = make_float4(dRGB.x, dRGB.y, dRGB.z, dL_dmean.x);
+            pk[1] = make_float4(dL_dmean.y, dL_dmean.z, dL_dopacity, dL_dseg.x);
+            pk[2] = make_float4(dL_dseg.y, dL_dscale.x, dL_dscale.y, dL_dscale.z);
+            pk[3] = dL_drot;
             if (a.out.dL_dmeans2D) { // per-view screen-space gradient for the densification statistics (dense, pre-zeroed)
                 a.out.dL_dmeans2D[3 * (size_t)idx + 0] = dL_dmean2D.x;
                 a.out.dL_dmeans2D[3 * (size_t)idx + 1] = dL_dmean2D.y;
@@ -517,97 +513,6 @@ __global__ void __launch_bounds__(BWD_THREADS) preprocess_bwd_kernel(const PreBw
     }
 }
 
-// Receiving side of the multi-GPU gradient exchange: ADD one view's packets into dense gradient rows. A warp owns 32
-// packets; the 192-B SH rows are rebuilt as basis(dir) x dL_dRGB and added row-cooperatively (coalesced bursts).
-constexpr int APPLY_THREADS = 128;
-__global__ void __launch_bounds__(APPLY_THREADS) apply_packets_kernel(const ApplyPacketsArgs a)
-{
-    __shared__ float s_w[APPLY_THREADS / 32][32][20]; // per packet: 16 basis weights + dRGB
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * APPLY_THREADS + threadIdx.x;
-    const uint32_t n = min(*a.count, a.capacity);
-    if ((r & ~31u) >= n) return;
-    const bool valid = r < n;
-    uint32_t id = 0;
-    float f[GSR_PACKET_WORDS];
-#pragma unroll
-    for (int k = 0; k < GSR_PACKET_WORDS; k++) f[k] = 0.f;
-    if (valid) {
-        const uint32_t* pk = a.packets + (size_t)r * GSR_PACKET_WORDS;
-        id = pk[0];
-#pragma unroll
-        for (int k = 1; k < GSR_PACKET_WORDS; k++) f[k] = __uint_as_float(pk[k]);
-    }
-    const size_t i = (size_t)id;
-    if (a.out.dL_dsh && a.M > 0) {
-        float w[16];
-        if (valid) {
-            const float3 pos = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
-            V3 dir_orig = {pos.x - a.campos[0], pos.y - a.campos[1], pos.z - a.campos[2]};
-            const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-            sh_basis(a.D, dir_orig.x / len, dir_orig.y / len, dir_orig.z / len, w);
-#pragma unroll
-            for (int k = 0; k < 16; k++) s_w[warp][lane][k] = w[k];
-            s_w[warp][lane][16] = f[1];
-            s_w[warp][lane][17] = f[2];
-            s_w[warp][lane][18] = f[3];
-        }
-        __syncwarp();
-        const uint32_t nrows = min(32u, n - (r & ~31u));
-        const int row_floats = a.M * 3;
-        // 4 rows per trip: the 8 loads of a trip are issued before the first add (the read-modify-write is latency bound)
-        for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
-            float* dst[4];
-            float cur[4][2];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t rr = min(r0 + u, nrows - 1);
-                const uint32_t id_rr = __shfl_sync(0xffffffffu, id, rr);
-                dst[u] = a.out.dL_dsh + (size_t)id_rr * row_floats;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int k = (int)lane + 32 * h;
-                    cur[u][h] = (r0 + u < nrows && k < row_floats) ? dst[u][k] : 0.f;
-                }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int k = (int)lane + 32 * h;
-                    if (r0 + u < nrows && k < row_floats) {
-                        const int coef = k / 3, ch = k - 3 * coef;
-                        if (coef < 16) dst[u][k] = cur[u][h] + s_w[warp][r0 + u][coef] * s_w[warp][r0 + u][16 + ch];
-                    }
-                }
-        }
-    }
-    if (!valid) return;
-    if (a.out.dL_dmeans3D) {
-        a.out.dL_dmeans3D[3 * i + 0] += f[4];
-        a.out.dL_dmeans3D[3 * i + 1] += f[5];
-        a.out.dL_dmeans3D[3 * i + 2] += f[6];
-    }
-    if (a.out.dL_dopacity) a.out.dL_dopacity[i] += f[7];
-    if (a.out.dL_dsegments && a.S == 2) {
-        a.out.dL_dsegments[2 * i + 0] += f[8];
-        a.out.dL_dsegments[2 * i + 1] += f[9];
-    }
-    if (a.out.dL_dscales) {
-        a.out.dL_dscales[3 * i + 0] += f[10];
-        a.out.dL_dscales[3 * i + 1] += f[11];
-        a.out.dL_dscales[3 * i + 2] += f[12];
-    }
-    if (a.out.dL_drotations) {
-        a.out.dL_drotations[4 * i + 0] += f[13];
-        a.out.dL_drotations[4 * i + 1] += f[14];
-        a.out.dL_drotations[4 * i + 2] += f[15];
-        a.out.dL_drotations[4 * i + 3] += f[16];
-    }
-}
-
 // Multi-GPU gradient rebuild, gather form: one thread per Gaussian sums the packets of all views that saw it and writes its dense
 // rows once. A warp owns 32 consecutive Gaussians = one word of every view's visibility index, so "which views, which packet"
 // costs two warp-uniform word loads per view, and the packets a warp needs from one view are adjacent in memory. Compared with
@@ -615,10 +520,13 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_packets_kernel(const Appl
 constexpr int GATHER_THREADS = 128;
 constexpr int GATHER_GROUP = 8; // views whose index words are loaded together (one lane per view)
 constexpr int GATHER_CAP = 64;  // packets a warp stages at a time (8 views x 32 Gaussians x ~20% visible = ~51)
+constexpr int GATHER_STRIDE = 20; // words between staged packets: 16-byte aligned, and 8 consecutive packets cover all 32 banks
 
-__device__ __forceinline__ void cp_async_4(uint32_t* smem_dst, const uint32_t* gmem_src)
+// 16-byte asynchronous copy, L2 only (.cg): packets are read once, and for a peer blob the request crosses NVLink as one
+// 16-byte read per lane, 64 contiguous bytes per packet (round 1 moved the 68-byte packets as 4-byte .ca copies)
+__device__ __forceinline__ void cp_async_16(uint32_t* smem_dst, const uint32_t* gmem_src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -633,7 +541,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
 {
     __shared__ __align__(16) uint32_t s_buf[GATHER_THREADS / 32][32 * SH_ROW_STRIDE]; // staging, then the SH rows for the coalesced store
     __shared__ float s_cam[GSR_MAX_GATHER_VIEWS * 3];
-    static_assert(GATHER_CAP * GSR_PACKET_WORDS <= 32 * SH_ROW_STRIDE, "staging must fit");
+    static_assert(GATHER_CAP * GATHER_STRIDE <= 32 * SH_ROW_STRIDE && GSR_PACKET_WORDS == 16, "staging must fit");
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < a.num_views * 3; i += GATHER_THREADS) s_cam[i] = a.campos[i];
     __syncthreads();
@@ -686,13 +594,13 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
             uint32_t m = 0u;                     // views of this segment that see my Gaussian
             for (uint32_t u = u0; u < e; u++) {
                 const uint32_t b_u = __shfl_sync(0xffffffffu, my_bits, u);
-                const uint32_t nwords = __popc(b_u) * GSR_PACKET_WORDS;
-                if (nwords == 0u) continue;
+                const uint32_t nquads = __popc(b_u) * (GSR_PACKET_WORDS / 4); // 16-byte quarters of this view's adjacent packets
+                if (nquads == 0u) continue;
                 const uint32_t f_u = __shfl_sync(0xffffffffu, my_first, u);
                 const uint32_t off_u = __shfl_sync(0xffffffffu, incl - my_cnt, u) - base;
                 const uint32_t* src = a.views[g0 + u] + a.packet_off + (size_t)f_u * GSR_PACKET_WORDS;
-                uint32_t* dst = stage + off_u * GSR_PACKET_WORDS;
-                for (uint32_t wd = lane; wd < nwords; wd += 32) cp_async_4(dst + wd, src + wd);
+                uint32_t* dst = stage + off_u * GATHER_STRIDE;
+                for (uint32_t qd = lane; qd < nquads; qd += 32) cp_async_16(dst + (qd >> 2) * GATHER_STRIDE + (qd & 3u) * 4u, src + qd * 4u);
                 m |= ((b_u >> lane) & 1u) << u;
             }
             if (!valid) m = 0u;
@@ -704,12 +612,14 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
                 const uint32_t off_u = __shfl_sync(0xffffffffu, incl - my_cnt, u) - base;
                 if (m) {
                     m &= m - 1u;
-                    const uint32_t* pk = stage + (off_u + __popc(b_u & lt_mask)) * GSR_PACKET_WORDS; // stride 17 words: conflict-free
+                    const float4* pk = reinterpret_cast<const float4*>(stage + (off_u + __popc(b_u & lt_mask)) * GATHER_STRIDE);
+                    const float4 p0 = pk[0], p1 = pk[1], p2 = pk[2], p3 = pk[3];
+                    const float f[13] = {p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, p3.z, p3.w};
 #pragma unroll
-                    for (int k = 0; k < 13; k++) acc[k] += __uint_as_float(pk[4 + k]);
+                    for (int k = 0; k < 13; k++) acc[k] += f[k];
                     if (want_sh) {
                         const int r = g0 + (int)u;
-                        const float cr = __uint_as_float(pk[1]), cg = __uint_as_float(pk[2]), cb = __uint_as_float(pk[3]);
+                        const float cr = p0.x, cg = p0.y, cb = p0.z;
                         V3 dir_orig = {pos.x - s_cam[3 * r], pos.y - s_cam[3 * r + 1], pos.z - s_cam[3 * r + 2]};
                         const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
                         float w[16];
@@ -857,12 +767,6 @@ int launch_preprocess_bwd(const PreBwdArgs& a, cudaStream_t s)
     PreBwdArgs b = a;
     b.fill = (!a.packets && !a.out.accumulate && fill_in_kernel() && !a.has_subset) ? 1 : 0;
     preprocess_bwd_kernel<<<a.g.nblk, BWD_THREADS, 0, s>>>(b); count_launches(1);
-    return 0;
-}
-int launch_apply_packets(const ApplyPacketsArgs& a, cudaStream_t s)
-{
-    if (a.capacity == 0) return 0;
-    apply_packets_kernel<<<(a.capacity + APPLY_THREADS - 1) / APPLY_THREADS, APPLY_THREADS, 0, s>>>(a); count_launches(1);
     return 0;
 }
 int launch_gather_packets(const GatherPacketsArgs& a, cudaStream_t s)

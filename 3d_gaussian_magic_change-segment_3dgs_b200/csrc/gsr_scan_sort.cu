@@ -323,6 +323,8 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_sort_coop_kernel(const Ra
 // inclusive prefix. Tiles are handed out by an atomic ticket, so every predecessor of a running tile is running or done and the
 // walk cannot dead-lock. Ranking inside the tile is the stable match.any scheme of tile_scatter_body.
 constexpr uint32_t LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_VAL = (1u << 30) - 1u;
+// Keys per thread of the look-back passes (tile = 256 x LB_PER_THREAD keys): larger tiles amortise the look-back walk and the
+// fixed per-tile work. GSR_LB_PT=8 selects 2048-key tiles for A/B runs.
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
 {
@@ -347,12 +349,14 @@ struct LookbackPassArgs
     uint32_t* ticket;            // zeroed
 };
 
+template <int LB_PER_THREAD>
 __global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(const LookbackPassArgs a)
 {
+    constexpr int LB_ITEMS = RADIX_THREADS * LB_PER_THREAD;
     __shared__ uint32_t s_cnt[8][256];
     __shared__ uint32_t s_gbase[256];
-    __shared__ uint32_t s_keys[RADIX_ITEMS];
-    __shared__ uint32_t s_vals[RADIX_ITEMS];
+    __shared__ uint32_t s_keys[LB_ITEMS];
+    __shared__ uint32_t s_vals[LB_ITEMS];
     __shared__ uint32_t s_warp[8], s_warp2[8];
     __shared__ uint32_t s_tile;
     const uint32_t n = a.n_dev ? min(*a.n_dev, a.n) : a.n;
@@ -360,23 +364,23 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(cons
     for (uint32_t i = threadIdx.x; i < 8 * 256; i += RADIX_THREADS) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t tile_base = tile * RADIX_ITEMS;
+    const uint32_t tile_base = tile * LB_ITEMS;
     if (tile_base >= n) return;
-    const uint32_t tile_n = min((uint32_t)RADIX_ITEMS, n - tile_base);
+    const uint32_t tile_n = min((uint32_t)LB_ITEMS, n - tile_base);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int shift = a.shift;
     const uint32_t mask = a.mask;
 
-    const uint32_t wbase = tile_base + warp * RADIX_WARP_ITEMS;
-    uint32_t key[RADIX_PER_THREAD], val[RADIX_PER_THREAD];
+    const uint32_t wbase = tile_base + warp * (LB_ITEMS / 8);
+    uint32_t key[LB_PER_THREAD], val[LB_PER_THREAD];
 #pragma unroll
-    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+    for (int k = 0; k < LB_PER_THREAD; k++) {
         const uint32_t i = wbase + k * 32 + lane;
         key[k] = i < n ? a.keys_in[i] : 0xffffffffu;
         val[k] = i < n ? a.vals_in[i] : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+    for (int k = 0; k < LB_PER_THREAD; k++) {
         const uint32_t i = wbase + k * 32 + lane;
         if (i < n) atomicAdd(&s_cnt[warp][(key[k] >> shift) & mask], 1u);
     }
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(cons
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < RADIX_PER_THREAD; k++) {
+    for (int k = 0; k < LB_PER_THREAD; k++) {
         const uint32_t i = wbase + k * 32 + lane;
         const bool valid = i < n;
         const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0x100u + lane;
@@ -557,7 +561,7 @@ namespace gsr
 size_t radix_lookback_ws_words(uint32_t n_cap, int nbits)
 {
     const int passes = radix_num_passes(nbits);
-    const size_t tiles = ((size_t)n_cap + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    const size_t tiles = ((size_t)n_cap + RADIX_ITEMS - 1) / RADIX_ITEMS; // sized for the smallest tile the passes may use
     return (size_t)passes * 256 + 32 + (size_t)passes * tiles * 256;
 }
 
@@ -582,13 +586,16 @@ int radix_sort_pairs_lookback(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, 
         return GSR_ERR_INVALID_ARGUMENT;
     }
     const int digit_bits = radix_digit_bits(nbits);
-    const uint32_t tiles = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
+    static const int pt = getenv("GSR_LB_PT") ? atoi(getenv("GSR_LB_PT")) : 16;
+    const uint32_t items = RADIX_THREADS * (uint32_t)(pt == 8 ? 8 : 16);
+    const uint32_t tiles = (n + items - 1) / items;
+    const uint32_t tiles_cap = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;
     uint32_t* hist = ws;
     uint32_t* tickets = ws + (size_t)passes * 256;
     uint32_t* status = tickets + 32;
     if (!hist_ready) {
         GSR_CUDA(cudaMemsetAsync(ws, 0, radix_lookback_ws_words(n, nbits) * sizeof(uint32_t), s));
-        const uint32_t grid = tiles < 1184u ? tiles : 1184u;
+        const uint32_t grid = tiles_cap < 1184u ? tiles_cap : 1184u;
         digit_hist_all_kernel<<<grid, RADIX_THREADS, 0, s>>>(keys[0], n, n_dev, passes, digit_bits, hist); count_launches(1);
     }
     int cur = 0;
@@ -596,8 +603,10 @@ int radix_sort_pairs_lookback(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, 
         LookbackPassArgs a;
         a.keys_in = keys[cur]; a.vals_in = vals[cur]; a.keys_out = keys[cur ^ 1]; a.vals_out = vals[cur ^ 1];
         a.n = n; a.n_dev = n_dev; a.shift = p * digit_bits; a.mask = (1u << digit_bits) - 1u;
-        a.digit_total = hist + p * 256; a.status = status + (size_t)p * tiles * 256; a.ticket = tickets + p;
-        radix_lookback_pass_kernel<<<tiles, RADIX_THREADS, 0, s>>>(a); count_launches(1);
+        a.digit_total = hist + p * 256; a.status = status + (size_t)p * tiles_cap * 256; a.ticket = tickets + p;
+        if (pt == 8) radix_lookback_pass_kernel<8><<<tiles, RADIX_THREADS, 0, s>>>(a);
+        else radix_lookback_pass_kernel<16><<<tiles, RADIX_THREADS, 0, s>>>(a);
+        count_launches(1);
         cur ^= 1;
     }
     return cur;

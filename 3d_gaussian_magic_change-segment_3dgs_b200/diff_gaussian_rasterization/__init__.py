@@ -373,9 +373,9 @@ def last_num_visible():
 
 def _backward_packets_native(rs, means3D, radii, segments, scales, rotations, grad_color, grad_segment, grad_depth, grad_alpha, sh,
                              geomBuffer, num_rendered, binningBuffer, imgBuffer, alpha, capacity, means2D_grad=None, raw=None, raw_params=None):
-    """gsr_backward_packets: the backward of one view as compact per-visible-Gaussian packets (17 words each, see
+    """gsr_backward_packets: the backward of one view as compact per-visible-Gaussian packets (16 words each, see
     include/gsr.h) instead of dense gradient rows. Returns (blob, count int32[1]): blob is ONE int32 tensor of
-    packet_index_words(P) + capacity * 17 words -- the view's visibility index followed by the packets -- i.e. the all-gather
+    packet_index_words(P) + capacity * 16 words -- the view's visibility index followed by the packets -- i.e. the all-gather
     payload of the view (see packet_blob_views). With raw=(packets_ptr, index_ptr) (device addresses, e.g. inside a
     gsr_peer_alloc buffer; room for `capacity` packets) the view is written there instead and blob is None.
     raw_params = {"sh_rest": _features_rest, "opacities": logits}: fused activations, packets carry raw-parameter gradients."""
@@ -434,7 +434,7 @@ def packet_blob_capacity(blob, P):
 
 
 def packet_blob_views(blob, P):
-    """(packets int32[capacity, 17], visible-bit words int32[W], first-packet-index words int32[W]) of a view blob (the index
+    """(packets int32[capacity, 16], visible-bit words int32[W], first-packet-index words int32[W]) of a view blob (the index
     is stored as pairs {bits, ~first}; `first` is only meaningful where bits != 0)."""
     W = (P + 31) // 32
     n = packet_index_words(P)
@@ -512,21 +512,6 @@ def peer_close(ptr, device):
 def peer_free(ptr, device):
     with torch.cuda.device(device):
         _lib.check(_lib.lib().gsr_peer_free(ctypes.c_void_p(ptr)), "gsr_peer_free")
-
-
-def apply_packets(means3D, campos, sh_degree, sh_coeffs, packets, count, out, num_class=NUM_CLASS):
-    """gsr_apply_packets: ADD one view's packets into the dense gradient tensors of `out` (dict with the native names
-    means3D / sh / segments / opacities / scales / rotations; missing or None entries are skipped)."""
-    L = _lib.lib()
-    device = means3D.device
-    P = means3D.size(0)
-    with torch.cuda.device(device):
-        g = lambda n: _ptr(out.get(n))
-        pg = GsrParamGrads(g("means3D"), None, g("sh"), None, g("segments"), g("opacities"), g("scales"), g("rotations"), None, 1)
-        cp = _prep(campos, device, "campos")
-        rc = L.gsr_apply_packets(P, int(sh_degree), int(sh_coeffs), int(num_class), means3D.data_ptr(), cp.data_ptr(), packets.data_ptr(),
-                                 int(packets.size(0)), count.data_ptr(), ctypes.byref(pg), torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(rc, "gsr_apply_packets")
 
 
 class _RasterizeGaussians(torch.autograd.Function):

@@ -167,7 +167,7 @@ def native_view_backward(D, leaves, rs, fwd, upstream, flat, first, means2D_grad
 # Sparse gradient exchange: each view's gradient is non-zero only on that view's visible Gaussians (~20%), and its
 # 48-float SH part is rank one. Ranks all-gather 68-byte packets (id + 16 floats) instead of all-reducing 244-byte dense rows,
 # and every rank rebuilds + sums the rows locally in the same (rank, view) order, so replicas stay bitwise identical.
-# Traffic per rank: (N-1) x 68 B x V_visible instead of ~2 x 244 B x P.
+# Traffic per rank: (N-1) x 64 B x V_visible instead of ~2 x 244 B x P.
 # ---------------------------------------------------------------------------------------------------------------------
 def native_view_backward_packets(D, leaves, rs, fwd, upstream, means2D_grad=None, capacity=0):
     """Backward of one view as packets. Returns (blob, count int32[1], V): blob = the view's all-gather payload (packets +
@@ -217,7 +217,7 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
     else:  # repack to the common capacity
         send = torch.empty((nv, words), dtype=torch.int32, device=device)
         for v, (blob, _, n) in enumerate(local_sets):
-            send[v, :nidx + n * 17].copy_(blob[:nidx + n * 17])
+            send[v, :nidx + n * D.PACKET_WORDS].copy_(blob[:nidx + n * D.PACKET_WORDS])
     if world > 1:
         recv = torch.empty((world * nv, words), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)

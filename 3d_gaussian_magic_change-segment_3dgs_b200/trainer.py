@@ -4,6 +4,8 @@ cameras per step, built from this package's pieces only --
     flat raw parameters (optim.FlatParameters)
       -> fused-activation forward (gsr_forward, raw_params)                          render()            train.py:106
       -> L1 + SSIM loss and its image gradient (gsr_image_loss)                      train.py:110-111
+      -> depth supervision from a monocular prior and its depth-image gradient        train.py:115-121 (using_depth, 'localrf'),
+         (gsr_depth_loss: median / quantile by radix select, fused normalisation)     utils/loss_utils.py:88-102
       -> backward into the flat gradient buffer / as packets (gsr_backward[_packets]) loss.backward()     train.py:143
       -> multi-GPU sum over all ranks' views (peer-memory gather, NCCL fallback)     (new: the reference is single-GPU)
       -> densification statistics per view, densify / prune / opacity reset          train.py:169-180
@@ -34,6 +36,7 @@ class OptimizationParams(NamedTuple):
     rotation_lr: float = 0.001
     percent_dense: float = 0.01
     lambda_dssim: float = 0.2
+    lambda_depth: float = 0.1  # weight of the depth-supervision term (using_depth, depth_loss_choice 'localrf')
     densification_interval: int = 100
     opacity_reset_interval: int = 3000
     densify_from_iter: int = 500
@@ -111,10 +114,12 @@ class NativeTrainer:
                                                     scale_modifier=1.0, viewmatrix=t("viewmatrix"), projmatrix=t("projmatrix"),
                                                     sh_degree=self.active_sh_degree, campos=t("campos"), prefiltered=False, debug=False)
 
-    def train_step(self, cams, gt_images):
+    def train_step(self, cams, gt_images, gt_depths=None):
         """One optimisation step over the batch `cams` (list of camera dicts: image_width/height, tanfovx/y, viewmatrix,
         projmatrix, campos -- the same list on every rank) with ground-truth images gt_images[i] ([3,H,W] CUDA, needed for this
-        rank's views only). Returns the batch-mean loss as a device scalar (all ranks' views, all-reduced)."""
+        rank's views only) and, optionally, monocular depth priors gt_depths[i] ([1,H,W] or None): the reference's using_depth
+        step, loss += compute_depth_loss(1 / render()["depth"].clamp(1e-6), gt_depth, lambda_depth) (train.py:115-121).
+        Returns the batch-mean loss as a device scalar (all ranks' views, all-reduced)."""
         o, D, dist = self.o, self.D, self.dist
         self.iteration += 1
         it = self.iteration
@@ -139,6 +144,11 @@ class NativeTrainer:
                 stats, g_color = losses.l1_ssim_loss_and_grad(fwd[1], gt_images[vi], o.lambda_dssim, grad_scale=1.0 / B)
                 total += stats[2] / B
                 up = {"color": g_color}
+                if gt_depths is not None and gt_depths[vi] is not None:  # viewpoint_cam.depth is not None and dataset.using_depth
+                    d_loss, g_depth = losses.depth_loss_and_grad(fwd[2], gt_depths[vi], o.lambda_depth, grad_scale=1.0 / B,
+                                                                 fused_from_raw_depth=True)
+                    total += d_loss[0] / B
+                    up["depth"] = g_depth
                 if dist is None:
                     mv.native_view_backward(D, v, rs, fwd, up, self.grads, first=(k == 0), means2D_grad=self._m2 if track else None)
                 elif self.px is not None:

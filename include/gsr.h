@@ -161,18 +161,19 @@ int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* rad
                  const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, gsr_stream_t stream);
 
 /* ---- multi-GPU gradient exchange (multi-view data parallelism) ----
- * Instead of dense rows, the backward can emit one compact PACKET per visible Gaussian of the view:
- *   word 0      Gaussian id (uint32)
- *   words 1-3   dL/dRGB of the SH colour, clamp mask applied      words 4-6   dL/dmean3D (all paths, incl. the SH view direction)
- *   word 7      dL/dopacity     words 8-9  dL/dsegment     words 10-12  dL/dscale     words 13-16  dL/drotation
- * 68 B instead of the 244-B dense row: the 48-float SH gradient row is rank one, basis(view direction) x dL/dRGB, and is
- * rebuilt by gsr_apply_packets on the receiving rank from the Gaussian's position and that view's camera centre.
- * Packets are ordered by Gaussian id; *count_dev receives the number of visible Gaussians. `capacity` must be >= the number of
+ * Instead of dense rows, the backward can emit one compact PACKET per visible Gaussian of the view, 16 floats = 64 bytes,
+ * 64-byte aligned (one 16-byte-vector copy per quarter):
+ *   words 0-2   dL/dRGB of the SH colour, clamp mask applied      words 3-5   dL/dmean3D (all paths, incl. the SH view direction)
+ *   word 6      dL/dopacity     words 7-8  dL/dsegment     words 9-11  dL/dscale     words 12-15  dL/drotation
+ * instead of the 244-B dense row: the 48-float SH gradient row is rank one, basis(view direction) x dL/dRGB, and is rebuilt by
+ * gsr_gather_packets on the receiving rank from the Gaussian's position and that view's camera centre. Packets carry no id:
+ * they are ordered by Gaussian id and the view's visibility index (below) maps a Gaussian to its packet.
+ * *count_dev receives the number of visible Gaussians. `capacity` must be >= the number of
  * visible Gaussians of the forward the state belongs to: with state->num_visible set, a smaller buffer fails with
  * GSR_ERR_OVERFLOW before anything is launched (with num_visible == 0 = unknown, packets beyond `capacity` are dropped and
  * *count_dev tells). dL_dmeans2D (optional, dense [P,3]) is overwritten for the
  * densification statistics. Requires shs + scales/rotations (the training configuration). */
-#define GSR_PACKET_WORDS 17
+#define GSR_PACKET_WORDS 16
 int gsr_backward_packets(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                          const GsrPixelGrads* pix, uint32_t* packets, uint32_t capacity, uint32_t* count_dev, float* dL_dmeans2D,
                          uint32_t* vis_index, void* scratch, size_t scratch_bytes, gsr_stream_t stream);
@@ -182,13 +183,10 @@ int gsr_backward_packets(const GsrView* view, const GsrGaussians* in, const int3
  * `first` is the packet index of the group's first visible Gaussian (packets are in ascending Gaussian order), so the packet
  * of Gaussian i is  first[i / 32] + popcount(bits[i / 32] & ((1 << (i % 32)) - 1)). A group without visible Gaussians is {0, 0}. */
 size_t gsr_packet_index_words(int32_t P);
-/* ADD the packets of one view (produced with camera centre `campos`, device [3]) into dense gradient rows. */
-int gsr_apply_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, const float* campos,
-                      const uint32_t* packets, uint32_t capacity, const uint32_t* count_dev, const GsrParamGrads* grads, gsr_stream_t stream);
 /* One pass over all Gaussians that SUMS the packets of `num_views` views (all-gathered from all ranks) into dense gradient
  * rows and WRITES every row (zeros where no view saw the Gaussian): no zero fill, no read-modify-write per view.
  * blobs: num_views view blobs, `blob_stride_words` apart; one blob = the view's vis_index (gsr_packet_index_words(P) words)
- * followed by [capacity][17] packet words -- exactly one all-gather payload per view. campos: [num_views][3] (device). Views are
+ * followed by [capacity][16] packet words -- exactly one all-gather payload per view. campos: [num_views][3] (device). Views are
  * summed in index order on every rank, so replicas end up bitwise identical. dL_dmeans2D / dL_dcolors / dL_dcov3D are ignored. */
 int gsr_gather_packets(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t num_class, const float* means3D, int32_t num_views,
                        const float* campos, const uint32_t* blobs, size_t blob_stride_words, uint32_t capacity,

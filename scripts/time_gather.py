@@ -1,4 +1,4 @@
-"""Times the gather-form packet rebuild (gsr_gather_packets) against the per-view read-modify-write form (gsr_apply_packets)
+"""Times the gather-form packet rebuild (gsr_gather_packets) (round 1 also timed a per-view read-modify-write form, since removed: 2.07 ms vs 0.75 ms for 8 views)
 for NV views of cfg3 on ONE GPU (no NCCL): python scripts/time_gather.py [NV]"""
 import importlib
 import os
@@ -46,16 +46,7 @@ def timeit(fn, n=10):
     return a.elapsed_time(b) / n
 
 
-def rmw():
-    flat.buffer.zero_()
-    for (blob, cnt, n), cp in zip(sets, campos):
-        D.apply_packets(gs["means3D"], cp, 3, 16, D.packet_blob_views(blob, P)[0], cnt, flat.backward_out())
-
-
 t_g = timeit(lambda: mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1))
-ref = flat.buffer.clone()
-t_r = timeit(rmw)
-err = float((flat.buffer - ref).abs().max() / ref.abs().max())
 st = {}
 mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1, state=st)
 sets2 = []
@@ -68,5 +59,4 @@ for v in range(NV):
 send = torch.stack([s[0] for s in sets2])
 cps = torch.stack(campos)
 t_k = timeit(lambda: D.gather_packets(gs["means3D"], cps, 3, 16, send, flat.backward_out()))
-print("views=%d visible=%s gather_exchange=%.3f ms gather_kernel_only=%.3f ms per_view_rmw=%.3f ms rel_diff=%.2e" %
-      (NV, [s[2] for s in sets], t_g, t_k, t_r, err))
+print("views=%d visible=%s gather_exchange=%.3f ms gather_kernel_only=%.3f ms" % (NV, [s[2] for s in sets], t_g, t_k))

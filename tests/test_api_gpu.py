@@ -190,7 +190,7 @@ def test_accumulate_mode_sums_views_into_flat_buffer():
 
 
 def test_gradient_packets_rebuild_dense_rows():
-    """gsr_backward_packets + gsr_gather_packets / gsr_apply_packets (the multi-GPU exchange format): rebuilding dense rows from
+    """gsr_backward_packets + gsr_gather_packets (the multi-GPU exchange format): rebuilding dense rows from
     a view's packets reproduces the dense backward (SH rows are rebuilt as basis(direction) x dL/dRGB) up to the fp32
     atomic-order noise between two backward runs; two views sum; the gather form overwrites every row."""
     import importlib
@@ -221,7 +221,7 @@ def test_gradient_packets_rebuild_dense_rows():
         assert int(sets[-1][1]) == sets[-1][2] == int((radii > 0).sum())
         pk, bits, first = D.packet_blob_views(sets[-1][0], P)
         vis_ids = torch.nonzero(radii > 0).flatten()
-        assert torch.equal(pk[:len(vis_ids), 0].long(), vis_ids)  # packets are in ascending Gaussian order
+        assert pk.shape[1] == 16  # 64-byte packets, no id word: ascending Gaussian order + the visibility index address them
         vis = torch.zeros(32 * bits.numel(), dtype=torch.bool, device="cuda")
         vis[:P] = radii > 0
         grp = vis.view(-1, 32)
@@ -245,11 +245,6 @@ def test_gradient_packets_rebuild_dense_rows():
     mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1)
     for leaf, nat in names.items():
         assert H.rel_linf(flat.views[leaf], dense[0][nat] + dense[1][nat]) <= 2e-5, leaf
-    # per-view read-modify-write form (gsr_apply_packets) on a zeroed buffer gives the same sums
-    rmw = mv.FlatGradients(P, "cuda")
-    for (blob, cnt, n), cp in zip(sets, campos):
-        D.apply_packets(gs["means3D"], cp, 3, 16, D.packet_blob_views(blob, P)[0], cnt, rmw.backward_out())
-    assert H.rel_linf(rmw.packed(), flat.packed()) <= 1e-6
     # sticky capacity: the second step's blobs are produced at the exchange's capacity and gathered without repacking
     st = {}
     mv.exchange_packets(D, None, flat, gs, sets, [campos], 3, world=1, state=st)

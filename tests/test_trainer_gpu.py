@@ -79,6 +79,46 @@ def test_native_trainer_matches_reference_style_loop():
     tr.close()
 
 
+def test_native_trainer_depth_supervised_step_matches_reference_style_loop():
+    """The using_depth step (train.py:115-121, 'localrf'): render -> L1 + SSIM + compute_depth_loss(1 / depth.clamp(1e-6), prior) ->
+    backward, natively (gsr_depth_loss fused with render()'s depth normalisation) against the same step written with torch ops."""
+    import test_depth_loss_gpu as TD
+
+    Pk = H.pkg()
+    trainer = importlib.import_module(H.PKG_NAME + ".trainer")
+    D = Pk.diff_gaussian_rasterization
+    P, W, Hh = 30_000, 320, 240
+    raw0, cam0 = TR._raw_scene(P, W, Hh, 23)
+    cam = _cam_dict(cam0, W, Hh)
+    g = torch.Generator().manual_seed(9)
+    gt, prior = torch.rand(3, Hh, W, generator=g).cuda(), torch.rand(1, Hh, W, generator=g).cuda()
+    o = trainer.OptimizationParams()
+    init = {"means3D": raw0["xyz"], "features_dc": raw0["features_dc"], "features_rest": raw0["features_rest"], "segments": raw0["segment"],
+            "opacities": raw0["opacity"], "scales": raw0["scaling"], "rotations": raw0["rotation"]}
+    tr = trainer.NativeTrainer(D, init, o, cameras_extent=5.0, bg=torch.zeros(3))
+    tr.active_sh_degree = 3
+    p0 = {k: v.clone() for k, v in tr.params.views.items()}
+    native = float(tr.train_step([cam], [gt], [prior]))
+    # the same step in torch: activations -> classic rasterizer -> render()'s depth normalisation -> the reference's losses
+    tp = {k: v.clone().requires_grad_(True) for k, v in init.items()}
+    raw_t = {"xyz": tp["means3D"], "features_dc": tp["features_dc"], "features_rest": tp["features_rest"], "segment": tp["segments"],
+             "opacity": tp["opacities"], "scaling": tp["scales"], "rotation": tp["rotations"]}
+    act = TR._activate(raw_t)
+    rs = H.settings(cam, torch.zeros(3))
+    color, radii, depth, alpha, segment = Pk.GaussianRasterizer(rs)(means3D=act["means3D"], means2D=torch.zeros_like(tp["means3D"]),
+                                                                    opacities=act["opacities"], shs=act["shs"], segments=act["segments"],
+                                                                    scales=act["scales"], rotations=act["rotations"])
+    dn = depth / (depth.max() + 1e-5)  # gaussian_renderer/__init__.py:375
+    loss = TL._ref_loss(color, gt, o.lambda_dssim)[0] + TD._torch_depth_loss(1 / dn.clamp(1e-6), prior, o.lambda_depth)
+    loss.backward()
+    assert abs(native - float(loss.detach())) <= 2e-5 * max(1.0, abs(float(loss.detach())))
+    # the gradient the native step produced (it is still in the flat buffer) against autograd's
+    for k, view in tr.grads.views.items():
+        assert H.rel_linf(view, tp[k].grad.reshape(view.shape)) <= 2e-4, k
+    assert any(not torch.equal(tr.params.views[k], p0[k]) for k in p0)  # and the step was applied
+    tr.close()
+
+
 def test_native_trainer_densifies_and_keeps_running():
     Pk = H.pkg()
     trainer = importlib.import_module(H.PKG_NAME + ".trainer")

@@ -400,7 +400,8 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
         return GSR_ERR_INVALID_ARGUMENT;
     }
     g_timer.mark(s, "tile_sort");
-    rc = launch_tile_ranges(tkeys[tres], R, img.ranges, T, s);
+    static const bool use_tile_order = getenv("GSR_TILE_ORDER") && atoi(getenv("GSR_TILE_ORDER")) != 0;
+    rc = launch_tile_ranges(tkeys[tres], R, img.ranges, use_tile_order ? img.tile_order : nullptr, T, s);
     if (rc) return rc;
     GSR_LAUNCHED(s, debug, "tile_ranges");
     g_timer.mark(s, "tile_ranges");
@@ -409,7 +410,7 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     RenderArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.W = W; ra.H = H; ra.grid_x = gx; ra.grid_y = gy;
-    ra.ranges = img.ranges; ra.point_list = b.point_list; ra.rec = g.rec; ra.bg = view->bg;
+    ra.ranges = img.ranges; ra.tile_order = use_tile_order ? img.tile_order : nullptr; ra.point_list = b.point_list; ra.rec = g.rec; ra.bg = view->bg;
     ra.out_color = out->color; ra.out_segment = out->segment; ra.out_depth = out->depth; ra.out_alpha = out->alpha;
     ra.n_contrib = img.n_contrib;
     launch_render_fwd(ra, view->num_class, s);
@@ -627,7 +628,8 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     RenderArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.W = W; ra.H = H; ra.grid_x = gx; ra.grid_y = gy;
-    ra.ranges = img.ranges; ra.point_list = (const uint32_t*)state->binning; ra.rec = g.rec; ra.bg = view->bg;
+    static const bool use_tile_order_b = getenv("GSR_TILE_ORDER") && atoi(getenv("GSR_TILE_ORDER")) != 0;
+    ra.ranges = img.ranges; ra.tile_order = use_tile_order_b ? img.tile_order : nullptr; ra.point_list = (const uint32_t*)state->binning; ra.rec = g.rec; ra.bg = view->bg;
     ra.n_contrib = img.n_contrib; ra.alphas = alpha;
     ra.dL_dcolor = pix->dL_dcolor; ra.dL_dsegment = pix->dL_dsegment; ra.dL_ddepth = pix->dL_ddepth; ra.dL_dalpha = pix->dL_dalpha;
     ra.grad_rec = grad_rec;

@@ -58,8 +58,9 @@ struct BinState
 
 struct ImgState
 {
-    uint32_t* n_contrib; // [H*W]
-    uint2* ranges;       // [T]
+    uint32_t* n_contrib;  // [H*W]
+    uint2* ranges;        // [T]
+    uint32_t* tile_order; // [T] tile ids by descending list length: CTA i of the compositing kernels takes tile tile_order[i]
 };
 
 constexpr int RADIX_ITEMS = 2048;  // keys per radix CTA (256 threads x 8)
@@ -123,6 +124,7 @@ inline size_t img_layout(char* base, size_t N, size_t T, ImgState& s)
     char* p = base;
     carve(p, s.n_contrib, N);
     carve(p, s.ranges, T);
+    carve(p, s.tile_order, T);
     return (size_t)(p - base) + 256;
 }
 
@@ -236,6 +238,7 @@ struct RenderArgs
 {
     int W, H, grid_x, grid_y;
     const uint2* ranges;
+    const uint32_t* tile_order; // longest lists first (launch_tile_ranges)
     const uint32_t* point_list;
     const float4* rec;
     const float* bg;
@@ -267,7 +270,7 @@ int launch_instance_offsets(const GeomState& g, const BinState& b, uint32_t V, u
 // (tile id, slot) per instance in depth order + digit totals of the tile sort's passes (hist: [passes][256], zeroed)
 int launch_emit(const GeomState& g, const BinState& b, uint32_t V, uint32_t R, const uint32_t* sorted_slots, int grid_x, int digit_bits, int passes,
                 uint32_t* hist, uint32_t* out_keys, uint32_t* out_vals, cudaStream_t s);
-int launch_tile_ranges(const uint32_t* sorted_tile_keys, uint32_t R, uint2* ranges, uint32_t T, cudaStream_t s);
+int launch_tile_ranges(const uint32_t* sorted_tile_keys, uint32_t R, uint2* ranges, uint32_t* tile_order, uint32_t T, cudaStream_t s);
 int launch_render_fwd(const RenderArgs& a, int S, cudaStream_t s);
 int launch_render_bwd(const RenderArgs& a, int S, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);

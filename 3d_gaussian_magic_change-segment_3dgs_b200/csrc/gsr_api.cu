@@ -231,8 +231,12 @@ static int validate(const GsrView* view, const GsrGaussians* in)
             return GSR_ERR_INVALID_ARGUMENT;
         }
     }
-    if (view->num_class != 0 && view->num_class != 2) {
-        set_error("num_class=%d is not built (the reference is compiled with NUM_CLASS=2; 0 disables segments)", view->num_class);
+    if (view->num_class < 0 || view->num_class > GSR_MAX_NUM_CLASS) {
+        set_error("num_class=%d: 0 (no segments) .. %d", view->num_class, GSR_MAX_NUM_CLASS);
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (view->num_class > 2 && in->num_parts > 0) {
+        set_error("fused sub-scenes (parts) render at most 2 segment classes");
         return GSR_ERR_UNSUPPORTED;
     }
     const int gx = (view->image_width + TILE_X - 1) / TILE_X, gy = (view->image_height + TILE_Y - 1) / TILE_Y;
@@ -275,7 +279,7 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     if (rc) return rc;
     if (num_rendered) *num_rendered = 0;
     if (in->P == 0 || (in->subset && in->subset_count == 0)) return 0;
-    if (!out || !out->color || !out->depth || !out->alpha || !out->radii || (view->num_class == 2 && !out->segment) || !alloc) {
+    if (!out || !out->color || !out->depth || !out->alpha || !out->radii || (view->num_class > 0 && !out->segment) || !alloc) {
         set_error("missing output pointers or allocator");
         return GSR_ERR_INVALID_ARGUMENT;
     }
@@ -294,7 +298,7 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
 
     // ---- state buffers whose size is known up front ----
     GeomState g;
-    const size_t geom_bytes = geom_layout(nullptr, P, g);
+    const size_t geom_bytes = geom_layout(nullptr, P, g, view->num_class);
     char* geom_base = (char*)alloc(alloc_user, GSR_BUF_GEOM, geom_bytes);
     ImgState img;
     const size_t img_bytes = img_layout(nullptr, N, T, img);
@@ -303,7 +307,7 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
         set_error("state allocation failed (geom %zu B, img %zu B)", geom_bytes, img_bytes);
         return GSR_ERR_ALLOC;
     }
-    geom_layout(geom_base, P, g);
+    geom_layout(geom_base, P, g, view->num_class);
     img_layout(img_base, N, T, img);
 
     GSR_CUDA(cudaMemsetAsync(g.counters, 0, CNT_WORDS * sizeof(uint32_t), s));
@@ -413,19 +417,38 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     ra.ranges = img.ranges; ra.tile_order = use_tile_order ? img.tile_order : nullptr; ra.point_list = b.point_list; ra.rec = g.rec; ra.bg = view->bg;
     ra.out_color = out->color; ra.out_segment = out->segment; ra.out_depth = out->depth; ra.out_alpha = out->alpha;
     ra.n_contrib = img.n_contrib;
-    launch_render_fwd(ra, view->num_class, s);
+    ra.seg_count = view->num_class >= 2 ? 2 : view->num_class;
+    launch_render_fwd(ra, view->num_class > 0 ? 2 : 0, s);
     GSR_LAUNCHED(s, debug, "render_fwd");
+    // runtime class count (the reference compiles NUM_CLASS = 2 in, config.h:16; its ModelParams default to 29 classes): the
+    // record carries channels 0-1, every further pair of channels is composited by one more pass over the same lists
+    for (uint32_t k = 0; k < g.extra_pairs; k++) {
+        const int c0 = 2 * ((int)k + 1);
+        if (!in->segments) {
+            GSR_CUDA(cudaMemsetAsync(out->segment + (size_t)c0 * N, 0, (size_t)(view->num_class - c0) * N * sizeof(float), s));
+            break;
+        }
+        RenderArgs rk = ra;
+        rk.out_color = nullptr; rk.out_depth = nullptr; rk.out_alpha = nullptr; rk.n_contrib = nullptr;
+        rk.out_segment = out->segment + (size_t)c0 * N;
+        rk.seg_src = g.seg_extra + (size_t)k * g.slots;
+        rk.seg_count = view->num_class - c0 >= 2 ? 2 : 1;
+        launch_render_fwd(rk, 2, s);
+        GSR_LAUNCHED(s, debug, "render_fwd (segment pair)");
+    }
     g_timer.mark(s, "render_fwd");
     g_timer.finish(s, 0);
     return 0;
 }
 
-extern "C" size_t gsr_backward_scratch_bytes(int32_t P)
+extern "C" size_t gsr_backward_scratch_bytes_n(int32_t P, int32_t num_class)
 {
     if (P <= 0) return 0;
     const size_t nblk = ((size_t)P + PRE_BLOCK - 1) / PRE_BLOCK;
-    return nblk * PRE_BLOCK * GRAD_REC_FLOATS * sizeof(float) + 256;
+    const size_t extra = num_class > 2 ? (size_t)((num_class + 1) / 2 - 1) : 0; // dL/dsegment of the channel pairs beyond the record's
+    return nblk * PRE_BLOCK * (GRAD_REC_FLOATS + 2 * extra) * sizeof(float) + 512;
 }
+extern "C" size_t gsr_backward_scratch_bytes(int32_t P) { return gsr_backward_scratch_bytes_n(P, 2); }
 
 static int backward_impl(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                          const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, cudaStream_t s,
@@ -568,9 +591,13 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
         set_error("gsr_backward: binning state missing");
         return GSR_ERR_INVALID_ARGUMENT;
     }
-    if (scratch_bytes < gsr_backward_scratch_bytes(count)) {
-        set_error("gsr_backward: scratch too small (%zu < %zu)", scratch_bytes, gsr_backward_scratch_bytes(count));
+    if (scratch_bytes < gsr_backward_scratch_bytes_n(count, view->num_class)) {
+        set_error("gsr_backward: scratch too small (%zu < %zu)", scratch_bytes, gsr_backward_scratch_bytes_n(count, view->num_class));
         return GSR_ERR_INVALID_ARGUMENT;
+    }
+    if (packets && view->num_class != 0 && view->num_class != 2) {
+        set_error("gsr_backward_packets carries 2 segment classes (num_class=%d)", view->num_class);
+        return GSR_ERR_UNSUPPORTED;
     }
     const bool debug = view->debug != 0;
     const int P = in->P, W = view->image_width, H = view->image_height;
@@ -578,10 +605,11 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     const uint32_t T = (uint32_t)gx * (uint32_t)gy;
 
     GeomState g;
-    geom_layout((char*)state->geom, count, g);
+    geom_layout((char*)state->geom, count, g, view->num_class);
     ImgState img;
     img_layout((char*)state->img, (size_t)W * H, T, img);
     float* grad_rec = (float*)align_up((size_t)scratch, 256);
+    float* grad_seg_extra = (float*)align_up((size_t)(grad_rec + (size_t)g.slots * GRAD_REC_FLOATS), 256);
 
     PreBwdArgs pb;
     pb.P = P; pb.D = view->sh_degree; pb.M = in->shs ? view->sh_coeffs : 0; pb.S = view->num_class;
@@ -591,7 +619,7 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     pb.W = W; pb.H = H; pb.tan_fovx = view->tanfovx; pb.tan_fovy = view->tanfovy;
     pb.focal_y = H / (2.0f * view->tanfovy);
     pb.focal_x = W / (2.0f * view->tanfovx);
-    pb.radii = radii; pb.g = g; pb.grad_rec = grad_rec; pb.out = *grads;
+    pb.radii = radii; pb.g = g; pb.grad_rec = grad_rec; pb.grad_seg_extra = reinterpret_cast<const float2*>(grad_seg_extra); pb.out = *grads;
     pb.colors_precomp_given = in->colors_precomp != nullptr;
     pb.packets = packets; pb.packet_capacity = capacity; pb.packet_count = count_dev; pb.vis_index = vis_index;
     pb.has_subset = in->subset != nullptr;
@@ -633,8 +661,25 @@ static int backward_impl(const GsrView* view, const GsrGaussians* in, const int3
     ra.n_contrib = img.n_contrib; ra.alphas = alpha;
     ra.dL_dcolor = pix->dL_dcolor; ra.dL_dsegment = pix->dL_dsegment; ra.dL_ddepth = pix->dL_ddepth; ra.dL_dalpha = pix->dL_dalpha;
     ra.grad_rec = grad_rec;
-    launch_render_bwd(ra, view->num_class, s);
+    ra.seg_count = view->num_class >= 2 ? 2 : view->num_class;
+    launch_render_bwd(ra, view->num_class > 0 ? 2 : 0, s);
     GSR_LAUNCHED(s, debug, "render_bwd");
+    if (g.extra_pairs && in->segments && pix->dL_dsegment) { // one more pass per further pair of segment channels (linear: grad_rec accumulates)
+        GSR_CUDA(cudaMemsetAsync(grad_seg_extra, 0, (size_t)g.extra_pairs * g.slots * 2 * sizeof(float), s));
+        for (uint32_t k = 0; k < g.extra_pairs; k++) {
+            const int c0 = 2 * ((int)k + 1);
+            RenderArgs rk = ra;
+            rk.dL_dcolor = nullptr; rk.dL_ddepth = nullptr; rk.dL_dalpha = nullptr;
+            rk.dL_dsegment = pix->dL_dsegment + (size_t)c0 * W * H;
+            rk.seg_src = g.seg_extra + (size_t)k * g.slots;
+            rk.seg_count = view->num_class - c0 >= 2 ? 2 : 1;
+            rk.grad_seg = grad_seg_extra + (size_t)k * g.slots * 2;
+            launch_render_bwd(rk, 2, s);
+            GSR_LAUNCHED(s, debug, "render_bwd (segment pair)");
+        }
+    } else if (g.extra_pairs) {
+        GSR_CUDA(cudaMemsetAsync(grad_seg_extra, 0, (size_t)g.extra_pairs * g.slots * 2 * sizeof(float), s));
+    }
     g_timer.mark(s, "render_bwd");
 
     if (fills_on_side) {

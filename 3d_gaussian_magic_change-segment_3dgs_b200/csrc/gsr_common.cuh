@@ -40,6 +40,10 @@ struct GeomState
     size_t dhist_words;
     uint32_t nblk;
     uint32_t slots;      // nblk * PRE_BLOCK
+    // num_class > 2: the record carries segment channels 0 and 1; channel pair k >= 1 of a slot lives in seg_extra[(k-1)*slots + slot]
+    // and is composited by one extra pass per pair (runtime class count; the reference compiles NUM_CLASS in, config.h:16)
+    float2* seg_extra;
+    uint32_t extra_pairs; // ceil(num_class / 2) - 1, or 0
 };
 
 struct BinState
@@ -78,7 +82,7 @@ inline void carve(char*& p, T*& out, size_t count)
     p += count * sizeof(T);
 }
 
-inline size_t geom_layout(char* base, int P, GeomState& g)
+inline size_t geom_layout(char* base, int P, GeomState& g, int num_class = 2)
 {
     char* p = base;
     g.nblk = (uint32_t)((P + PRE_BLOCK - 1) / PRE_BLOCK);
@@ -97,6 +101,8 @@ inline size_t geom_layout(char* base, int P, GeomState& g)
     // depth sort (32 bits = 4 passes, one kernel each): [4][256] digit totals | 32 tickets | [4][tiles][256] look-back words
     g.dhist_words = radix_lookback_ws_words(g.slots, 32);
     carve(p, g.dhist, g.dhist_words);
+    g.extra_pairs = num_class > 2 ? (uint32_t)((num_class + 1) / 2 - 1) : 0u; // carved LAST: the layout before it does not depend on num_class
+    carve(p, g.seg_extra, (size_t)g.extra_pairs * g.slots);
     return (size_t)(p - base) + 256;
 }
 
@@ -211,6 +217,7 @@ struct PreBwdArgs
     const int32_t* radii;
     GeomState g;
     const float* grad_rec; // [slots][12]
+    const float2* grad_seg_extra; // num_class > 2: [extra_pairs][slots] dL/dsegment of channel pairs 1.. (compositing backward, extra passes)
     GsrParamGrads out;
     bool colors_precomp_given;
     // packet mode (multi-GPU gradient exchange): one GSR_PACKET_WORDS record per visible Gaussian instead of dense rows
@@ -255,6 +262,11 @@ struct RenderArgs
     const float* dL_ddepth;
     const float* dL_dalpha;
     float* grad_rec;
+    // extra segment-pair passes (num_class > 2): the pair's per-slot values, how many of its two channels exist, and where the
+    // backward accumulates the pair's dL/dsegment (instead of columns 4-5 of grad_rec); out_* / dL_* other than segment are null
+    const float2* seg_src;
+    int seg_count;
+    float* grad_seg;
 };
 
 // ---- stage launchers (each defined next to its kernels) ----

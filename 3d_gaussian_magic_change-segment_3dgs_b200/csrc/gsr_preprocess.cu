@@ -113,6 +113,10 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
                         const float2 sg = *reinterpret_cast<const float2*>(in.segments + 2 * (size_t)gid);
                         s0 = a.raw ? act_sigmoid(sg.x) : sg.x;
                         s1 = a.raw ? act_sigmoid(sg.y) : sg.y;
+                    } else if (a.S > 0 && in.segments != nullptr) { // runtime class count: channels 0-1 here, the other pairs below
+                        const float* sg = in.segments + (size_t)a.S * gid;
+                        s0 = a.raw ? act_sigmoid(sg[0]) : sg[0];
+                        if (a.S > 1) s1 = a.raw ? act_sigmoid(sg[1]) : sg[1];
                     }
                     const float op = a.raw ? act_sigmoid(in.opacities[gid]) : in.opacities[gid];
                     radius_out = my_radius;
@@ -138,6 +142,15 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
         a.g.rect[slot] = rect;
         a.g.slot_gid[slot] = (uint32_t)(a.num_parts > 0 ? idx : gid); // the backward addresses inputs and gradient rows through this
         a.g.clamped[slot] = (uint8_t)clamp_bits;
+        for (uint32_t k = 0; k < a.g.extra_pairs; k++) { // num_class > 2: segment channel pairs 1.. of this slot
+            float2 v = {0.f, 0.f};
+            if (a.segments != nullptr) {
+                const float* sg = a.segments + (size_t)a.S * gid + 2 * (k + 1);
+                v.x = a.raw ? act_sigmoid(sg[0]) : sg[0];
+                if (2 * (k + 1) + 1 < (uint32_t)a.S) v.y = a.raw ? act_sigmoid(sg[1]) : sg[1];
+            }
+            a.g.seg_extra[(size_t)k * a.g.slots + slot] = v;
+        }
     }
     // instance count of the block -> global R (integer atomics: deterministic total)
     uint32_t t = tiles;
@@ -369,6 +382,10 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdArgs& a, const bo
             if (a.S == 2 && a.segments != nullptr) {
                 const float2 sg = *reinterpret_cast<const float2*>(a.segments + 2 * (size_t)idx);
                 dL_dseg = {dact_sigmoid(act_sigmoid(sg.x), dL_dseg.x), dact_sigmoid(act_sigmoid(sg.y), dL_dseg.y)};
+            } else if (a.S > 0 && a.segments != nullptr) {
+                const float* sg = a.segments + (size_t)a.S * idx;
+                dL_dseg.x = dact_sigmoid(act_sigmoid(sg[0]), dL_dseg.x);
+                if (a.S > 1) dL_dseg.y = dact_sigmoid(act_sigmoid(sg[1]), dL_dseg.y);
             }
         }
     }
@@ -453,6 +470,21 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdArgs& a, const bo
     if (a.out.dL_dsegments && a.S == 2) {
         put(a.out.dL_dsegments + 2 * i + 0, dL_dseg.x);
         put(a.out.dL_dsegments + 2 * i + 1, dL_dseg.y);
+    } else if (a.out.dL_dsegments && a.S > 0) { // runtime class count: pair 0 from the record, the other pairs from their own buffers
+        float* row = a.out.dL_dsegments + (size_t)a.S * i;
+        put(row, dL_dseg.x);
+        if (a.S > 1) put(row + 1, dL_dseg.y);
+        for (uint32_t k = 0; k < a.g.extra_pairs; k++) {
+            float2 gk = a.grad_seg_extra[((size_t)k * a.g.slots + slot)];
+            const int c0 = 2 * ((int)k + 1);
+            if (a.raw && a.segments != nullptr) {
+                const float* sg = a.segments + (size_t)a.S * i + c0;
+                gk.x = dact_sigmoid(act_sigmoid(sg[0]), gk.x);
+                if (c0 + 1 < a.S) gk.y = dact_sigmoid(act_sigmoid(sg[1]), gk.y);
+            }
+            put(row + c0, gk.x);
+            if (c0 + 1 < a.S) put(row + c0 + 1, gk.y);
+        }
     }
     if (a.out.dL_dscales) {
         put(a.out.dL_dscales + 3 * i + 0, dL_dscale.x);

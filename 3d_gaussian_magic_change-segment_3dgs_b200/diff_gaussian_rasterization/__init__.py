@@ -44,7 +44,8 @@ GsrPixelGrads, GsrState, GsrStateExport, GsrView = _lib.GsrPixelGrads, _lib.GsrS
 
 PACKET_WORDS = _lib.GSR_PACKET_WORDS
 NUM_CHANNELS = 3  # cuda_rasterizer/config.h:15
-NUM_CLASS = 2     # cuda_rasterizer/config.h:16 (segment channels rendered when `segments` is absent)
+NUM_CLASS = 2     # cuda_rasterizer/config.h:16 (segment channels rendered when `segments` is absent; with `segments` given the
+                  # class count is its second dimension, any value up to 64 -- a compile-time constant in the reference)
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -355,7 +356,7 @@ def _backward_native(rs, means3D, radii, colors_precomp, segments, scales, rotat
                            _ptr(grads["segments"]), _ptr(grads["opacities"]), _ptr(grads["scales"]), _ptr(grads["rotations"]),
                            _ptr(grads["cov3Ds_precomp"]), int(bool(accumulate)), _ptr(grads["sh_rest"]))
         state = GsrState(_ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), int(num_rendered), int(getattr(num_rendered, "num_visible", 0)))
-        nscratch = L.gsr_backward_scratch_bytes(count)
+        nscratch = L.gsr_backward_scratch_bytes_n(count, int(num_class))
         scratch = torch.empty(nscratch, dtype=torch.uint8, device=device)
         t_radii = radii.contiguous()
         t_alpha = _prep(alpha, device, "alpha")

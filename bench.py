@@ -24,7 +24,8 @@ bit-identical buffers).
 
 Printed JSON (rank 0, one line): `value` = views/s with everything resident in HBM (CUDA events, max over ranks);
 `e2e` = the same step driven from HOST buffers (camera matrices + ground-truth image and depth copied H2D from pinned memory
-every view, the reference's L1 + depth-supervision loss, loss scalar read back D2H); `roofline` = the dominant kernel against
+every view, the reference's using_depth training loss -- 0.8 L1 + 0.2 (1 - SSIM) + 0.1 compute_depth_loss, train.py:107-121 -- and
+its backward, loss scalar read back D2H; ours through this library's loss kernels, `--torch-loss` for the torch formulas); `roofline` = the dominant kernel against
 the peak that bounds it (compositing: FP32 issue, measured by in-run micro-benchmarks; streaming stages: measured HBM copy
 bandwidth); `cpu_baseline` = the C oracle (oracle/gsr_oracle.c, OpenMP) on a bounded sample of the same workload.
 
@@ -329,12 +330,30 @@ def pin_cameras(cams, device):
             cam[k + "_dev"] = cam[k].to(device)
 
 
-def train_loss(color, depth, gi, gd, depth_loss_fn):
-    """The reference's training loss shape with depth supervision (train.py:107-121, using_depth / localrf): L1 on the colour
-    (the SSIM term is the separate `gsr_image_loss` row) + compute_depth_loss(1 / (depth / (max + 1e-5)).clamp(1e-6),
-    gt_depth, 0.1)."""
-    dn = depth / (depth.max() + 1e-5)  # gaussian_renderer/__init__.py:375
-    return (color - gi).abs().mean() + depth_loss_fn(1 / dn.clamp(1e-6), gd, 0.1)
+def reference_photometric_loss(image, gt, lambda_dssim=0.2):
+    """(1 - lambda) * l1_loss + lambda * (1 - ssim) of train.py:110-111 with utils/loss_utils.py:104-150 restated in torch (11x11 Gaussian
+    window, sigma 1.5, zero padding, grouped conv2d) -- what the reference arm's e2e step runs."""
+    import torch.nn.functional as F
+
+    C = image.size(-3)
+    g = torch.tensor([np.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)], dtype=torch.float32)
+    g = (g / g.sum()).unsqueeze(1)
+    window = g.mm(g.t()).unsqueeze(0).unsqueeze(0).expand(C, 1, 11, 11).contiguous().to(image.device)
+    mu1, mu2 = F.conv2d(image, window, padding=5, groups=C), F.conv2d(gt, window, padding=5, groups=C)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(image * image, window, padding=5, groups=C) - mu1_sq
+    s2 = F.conv2d(gt * gt, window, padding=5, groups=C) - mu2_sq
+    s12 = F.conv2d(image * gt, window, padding=5, groups=C) - mu1_mu2
+    ssim_map = ((2 * mu1_mu2 + 0.01 ** 2) * (2 * s12 + 0.03 ** 2)) / ((mu1_sq + mu2_sq + 0.01 ** 2) * (s1 + s2 + 0.03 ** 2))
+    return (1.0 - lambda_dssim) * torch.abs(image - gt).mean() + lambda_dssim * (1.0 - ssim_map.mean())
+
+
+def reference_train_loss(color, depth, gi, gd):
+    """The reference's using_depth training loss (train.py:107-121, depth_loss_choice 'localrf') on the rasterizer's outputs:
+    (1 - 0.2) L1 + 0.2 (1 - SSIM) + compute_depth_loss(1 / render()['depth'].clamp(1e-6), gt_depth, 0.1), with render()'s
+    depth / (depth.max() + 1e-5) (gaussian_renderer/__init__.py:375)."""
+    dn = depth / (depth.max() + 1e-5)
+    return reference_photometric_loss(color, gi, 0.2) + reference_depth_loss(1 / dn.clamp(1e-6), gd, 0.1)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -440,7 +459,7 @@ def reference_arm(args, out):
                 continue
             means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
             color, radii, depth, alpha, segment = rasterize(rs, means2D)
-            loss = train_loss(color, depth, gi, gd, reference_depth_loss)
+            loss = reference_train_loss(color, depth, gi, gd)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
         if fwd_only:
@@ -494,7 +513,8 @@ def reference_arm(args, out):
                    "alg_bytes_per_step": bytes_step},
         "e2e": {"value": round(e2e_value, 4), "unit": "frames/s" if fwd_only else "it/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": round(ms_e2e / args.steps, 4), "loss": loss_host[0],
-                "loss_fn": "L1 colour + compute_depth_loss (median / quantile, utils/loss_utils.py:88-102) in torch"},
+                "loss_fn": "the reference's using_depth loss in torch: 0.8 L1 + 0.2 (1 - SSIM) (train.py:110-111) + compute_depth_loss "
+                           "(median / quantile, utils/loss_utils.py:88-102; train.py:118-121)"},
         "gpu_launches": 0, "clocks": clocks,
         "roofline": {"kernel": "whole step (reference CUDA)", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src},
@@ -650,9 +670,15 @@ def ours_arm(args, out):
     next_view = stage_views(cams, None if fwd_only else gt_img, gt_dep, device, torch.cuda.Stream(device=device))
     host_img = torch.empty(3, Hh, W).pin_memory() if fwd_only else None
     loss_host = [0.0]
-    depth_loss_fn = getattr(losses, "depth_loss", None) or reference_depth_loss
-    depth_loss_name = ("gsr_depth_loss (native median / quantile radix select)" if depth_loss_fn is not reference_depth_loss
-                       else "compute_depth_loss in torch")
+
+    def native_train_loss(color, depth, gi, gd):
+        """The same using_depth loss through this library's public loss API: gsr_image_loss + gsr_depth_loss (fused normalisation)."""
+        return losses.l1_ssim_loss(color, gi, 0.2) + losses.depth_supervision_loss(depth, gd, 0.1)
+
+    loss_fns = [reference_train_loss if args.torch_loss else native_train_loss]
+    loss_fn = lambda *xs: loss_fns[0](*xs)  # noqa: E731  (switched once below for the torch-loss side measurement)
+    depth_loss_name = ("the reference's formulas in torch (--torch-loss)" if args.torch_loss else
+                       "losses.l1_ssim_loss (gsr_image_loss) + losses.depth_supervision_loss (gsr_depth_loss: radix-select median / quantile)")
 
     def step_e2e():
         if fwd_only:
@@ -673,14 +699,14 @@ def ours_arm(args, out):
                 with torch.no_grad():
                     fwd = native_forward(rs)
                 color, depth = fwd[1].requires_grad_(True), fwd[2].requires_grad_(True)
-                loss = train_loss(color, depth, gi, gd, depth_loss_fn)
+                loss = loss_fn(color, depth, gi, gd)
                 loss.backward()  # pixel gradients only; the rasterizer backward runs natively into the flat buffer / as packets
                 with torch.no_grad():
                     flat_backward(rs, fwd, {"color": color.grad, "depth": depth.grad}, v, mode, sets)
             else:
                 means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
                 color, radii, depth, alpha, segment = rasterize(rs, means2D)
-                loss = train_loss(color, depth, gi, gd, depth_loss_fn)
+                loss = loss_fn(color, depth, gi, gd)
                 loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
         if use_flat:
@@ -712,6 +738,16 @@ def ours_arm(args, out):
     clocks = sampler.summary(timer.windows) if rank == 0 else None
     if rank == 0:
         sampler.stop()
+    # the same e2e step with the training loss computed by the reference's torch formulas: how much of `e2e` is the loss kernels
+    e2e_torch = None
+    if nranks == 1 and not fwd_only and not args.torch_loss and not args.no_stage_profile:
+        loss_fns[0] = reference_train_loss
+        k = max(3, min(10, args.steps))
+        ms_t = timer.run(step_e2e, k, 3, name="step_e2e_torch_loss")
+        loss_fns[0] = native_train_loss
+        e2e_torch = {"value": round(V * k / (ms_t / 1e3), 4), "unit": "it/s", "ms_per_step": round(ms_t / k, 4), "loss": loss_host[0],
+                     "what": "e2e with 0.8 L1 + 0.2 (1 - SSIM) + compute_depth_loss evaluated by torch ops (the reference's code path for the loss) "
+                             "instead of gsr_image_loss / gsr_depth_loss"}
 
     comm_ms = None
     if dist is not None and use_flat:
@@ -872,7 +908,8 @@ def ours_arm(args, out):
                    "alg_bytes_per_step": bytes_step},
         "e2e": {"value": round(e2e_value, 4), "unit": unit, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": round(ms_e2e / args.steps, 4), "loss": loss_host[0],
-                "loss_fn": "rendered image read back to pinned host memory" if fwd_only else "L1 colour + depth supervision: " + depth_loss_name},
+                "loss_fn": "rendered image read back to pinned host memory" if fwd_only else
+                "using_depth training loss (train.py:107-121): 0.8 L1 + 0.2 (1 - SSIM) + 0.1 compute_depth_loss, via " + depth_loss_name},
         "gpu_launches": launches_timed,
         "clocks": clocks,
         "roofline": roofline,
@@ -882,6 +919,8 @@ def ours_arm(args, out):
         "step_ms": timer.stats,
         "fwd_ms_per_frame": round(fwd_ms, 4),
     }
+    if e2e_torch is not None:
+        line["e2e_with_torch_loss"] = e2e_torch
     if micro is not None:
         line["microbench"] = micro
     if cfg4_1gpu is not None:
@@ -1002,6 +1041,8 @@ def main():
     ap.add_argument("--grad-exchange", default="peer", choices=["peer", "packets", "dense"],
                     help="N>1: peer = gather kernel pulls every rank's gradient packets over NVLink peer memory (default); "
                          "packets = NCCL all-gather of the packets, then the gather kernel; dense = all-reduce of the flat buffer")
+    ap.add_argument("--torch-loss", action="store_true", help="e2e leg: compute the training loss with the reference's torch formulas instead "
+                                                              "of this library's loss kernels (isolates the rasterizer's share of e2e)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-profile", action="store_true")
     ap.add_argument("--no-cfg4-base", action="store_true", help="skip the 8-views-per-step single-GPU measurement of the default N = 1 run")

@@ -30,6 +30,7 @@ extern "C" {
 #endif
 
 #define GSR_ABI_VERSION 3
+#define GSR_MAX_NUM_CLASS 64
 
 #define GSR_OK 0
 #define GSR_ERR_INVALID_ARGUMENT (-1)
@@ -56,7 +57,9 @@ typedef struct GsrView {
     float scale_modifier;
     int32_t sh_degree;   /* D: active degree 0..3 */
     int32_t sh_coeffs;   /* M: coefficients per Gaussian in `shs` (0 when shs == NULL) */
-    int32_t num_class;   /* channels of `segments` / out segment (reference NUM_CLASS = 2, config.h:16); 0 or 2 */
+    int32_t num_class;   /* channels of `segments` / out segment, 0 .. GSR_MAX_NUM_CLASS at run time (the reference compiles NUM_CLASS = 2 in,
+                            config.h:16, while its ModelParams default to 29): channels 0-1 ride in the splat record, every further pair is
+                            composited by one more pass over the same sorted lists, forward and backward */
     int32_t prefiltered;
     int32_t debug;       /* != 0: synchronise and check after every stage (auxiliary.h:166-173) */
     const float* bg;         /* [3] */
@@ -154,8 +157,10 @@ const char* gsr_last_error(void);
 int gsr_forward(const GsrView* view, const GsrGaussians* in, const GsrOutputs* out, gsr_alloc_fn alloc, void* alloc_user,
                 int32_t* num_rendered, gsr_stream_t stream);
 
-/* Bytes of scratch gsr_backward needs (per-Gaussian gradient records accumulated by the compositing backward). */
+/* Bytes of scratch gsr_backward needs (per-Gaussian gradient records accumulated by the compositing backward); the _n form for
+ * num_class > 2. P = rendered Gaussians (subset_count with an index list). */
 size_t gsr_backward_scratch_bytes(int32_t P);
+size_t gsr_backward_scratch_bytes_n(int32_t P, int32_t num_class);
 
 int gsr_backward(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                  const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, gsr_stream_t stream);

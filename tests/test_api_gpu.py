@@ -304,3 +304,57 @@ def test_unaligned_views_of_a_flat_buffer_are_accepted():
     out = H.run_ours(shifted, rs, export=False)
     for k in ["color", "depth", "alpha", "segment", "radii"]:
         assert torch.equal(out[k], ref[k]), k
+
+
+@pytest.mark.parametrize("N", [1, 5, 29])
+def test_runtime_class_count_equals_channel_pairs_of_the_two_class_path(N):
+    """num_class at run time (the reference compiles NUM_CLASS = 2 in, config.h:16, although its ModelParams default to 29): an
+    N-channel segment render equals the stack of 2-class renders of its channel pairs -- bit for bit in the forward -- and its
+    gradients equal the colour/depth/alpha gradient of one 2-class backward plus the segment-only gradients of every pair."""
+    Pk = H.pkg()
+    syn = H.synthetic()
+    P, W, Hh = 20_000, 208, 144
+    gs = H.to_dev(syn.make_gaussians(P, 33, num_class=2))
+    g = torch.Generator().manual_seed(N)
+    segN = torch.sigmoid(torch.randn(P, N, generator=g)).cuda()
+    cam = syn.make_camera(W, Hh)
+    rs = H.settings(cam, torch.tensor([0.1, 0.0, 0.2]))
+    up = H.to_dev(syn.upstream_grads(W, Hh, 3, with_depth=True, with_alpha=True))
+    up_seg = (torch.randn(N, Hh, W, generator=g) / (N * W * Hh)).cuda()
+    names = ["means3D", "opacities", "shs", "scales", "rotations"]
+
+    def run(seg, gseg, with_color):
+        lv = {k: gs[k].clone().requires_grad_(True) for k in names}
+        sg = seg.clone().requires_grad_(True)
+        m2 = torch.zeros(P, 3, device="cuda", requires_grad=True)
+        color, radii, depth, alpha, segment = Pk.GaussianRasterizer(rs)(means3D=lv["means3D"], means2D=m2, opacities=lv["opacities"], shs=lv["shs"],
+                                                                        segments=sg, scales=lv["scales"], rotations=lv["rotations"])
+        loss = (segment * gseg).sum()
+        if with_color:
+            loss = loss + (color * up["color"]).sum() + (depth * up["depth"]).sum() + (alpha * up["alpha"]).sum()
+        loss.backward()
+        grads = {k: lv[k].grad for k in names}
+        grads["means2D"], grads["segments"] = m2.grad, sg.grad
+        return (color, radii, depth, alpha, segment), grads
+
+    outN, gN = run(segN, up_seg, True)
+    assert outN[4].shape == (N, Hh, W) and gN["segments"].shape == (P, N)
+    want = {k: torch.zeros_like(v) for k, v in gN.items() if k != "segments"}
+    want_seg = torch.zeros(P, N, device="cuda")
+    for c0 in range(0, N, 2):
+        n = min(2, N - c0)
+        seg2 = torch.zeros(P, 2, device="cuda")
+        seg2[:, :n] = segN[:, c0:c0 + n]
+        g2 = torch.zeros(2, Hh, W, device="cuda")
+        g2[:n] = up_seg[c0:c0 + n]
+        out2, gr2 = run(seg2, g2, c0 == 0)
+        assert torch.equal(out2[4][:n], outN[4][c0:c0 + n]), c0  # every pair: bit-identical to the 2-class render
+        if c0 == 0:
+            for i in range(4):
+                assert torch.equal(out2[i], outN[i])
+        for k in want:
+            want[k] += gr2[k]
+        want_seg[:, c0:c0 + n] = gr2["segments"][:, :n]
+    for k in want:
+        assert H.rel_linf(gN[k], want[k]) <= 3e-5, k
+    assert H.rel_linf(gN["segments"], want_seg) <= 3e-5

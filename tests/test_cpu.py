@@ -189,7 +189,7 @@ def test_flat_buffer_layouts_and_packet_blob_helpers():
         assert float(fp.buffer[o:o + c].min()) == float(fp.buffer[o:o + c].max()) == float(i)
     assert mv.sh_coeffs_of(s.views) == 16 and mv.sh_coeffs_of(f.views) == 16
     assert set(optim.GROUPS.values()) == set(s.views)  # the reference's seven parameter groups
-    # view blobs: index first (2 words per 32 Gaussians, padded to 128 B), then 17-word packets, padded to 128 B
+    # view blobs: index first (2 words per 32 Gaussians, padded to 128 B), then 16-word (64-byte) packets, padded to 128 B
     for P2 in (1, 32, 33, 30_000):
         nidx = D.packet_index_words(P2)
         assert nidx % 32 == 0 and nidx >= 2 * ((P2 + 31) // 32)
@@ -198,7 +198,7 @@ def test_flat_buffer_layouts_and_packet_blob_helpers():
             blob = torch.zeros(words, dtype=torch.int32)
             assert words % 32 == 0 and cap <= D.packet_blob_capacity(blob, P2) <= cap + 2
             pk, bits, first = D.packet_blob_views(blob, P2)
-            assert pk.shape[1] == 17 and bits.numel() == first.numel() == (P2 + 31) // 32
+            assert pk.shape[1] == 16 and bits.numel() == first.numel() == (P2 + 31) // 32
 
 
 def test_graft_entry_build_runs():

@@ -3,7 +3,7 @@
     GSR_BWD_VARIANT=2 python scripts/ab_bwd.py save [cfg3]     # 2 pixels/lane scalar kernel (round 1): saves its gradients
     GSR_BWD_VARIANT=5 python scripts/ab_bwd.py cmp  [cfg3]     # packed fp32x2 kernel: stage times + max relative difference
 
-Prints the per-stage device times (gsr_set_profiling, CUDA events inside libgsr) averaged over 10 steps."""
+Prints the per-stage device times (gsr_set_profiling, CUDA events inside libgsr) median of 21 steps."""
 import json
 import os
 import sys
@@ -28,12 +28,13 @@ L = Pk._lib.lib()
 out = H.run_ours(gs, rs, ug, export=False)
 torch.cuda.synchronize()
 L.gsr_set_profiling(1)
-acc = {}
-for _ in range(10):
+samples = {}
+for _ in range(21):
     o = H.run_ours(gs, rs, ug, export=False)
     torch.cuda.synchronize()
     for k, v in Pk._lib.stage_times().items():
-        acc[k] = acc.get(k, 0.0) + v / 10
+        samples.setdefault(k, []).append(v)
+acc = {k: sorted(v)[len(v) // 2] for k, v in samples.items()}  # median: the first stage's event also sees allocator hiccups
 L.gsr_set_profiling(0)
 tag = os.environ.get("GSR_BWD_VARIANT", "default") + "/" + os.environ.get("GSR_FILL_STREAM", "side")
 print(json.dumps({"variant": tag, "workload": wl, "stages_ms": {k: round(v, 4) for k, v in acc.items()}}))

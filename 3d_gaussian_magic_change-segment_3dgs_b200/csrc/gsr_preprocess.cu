@@ -784,6 +784,38 @@ static bool fill_in_kernel()
     static const bool v = getenv("GSR_FILL_MODE") && !strcmp(getenv("GSR_FILL_MODE"), "kernel");
     return v;
 }
+// Zero fill of up to 10 dense gradient tensors in ONE launch, written for running BESIDE the compositing backward:
+//   * streaming stores (st.global.cs, evict-first): 1.46 GB of zeros do not push the backward's working set -- the per-tile lists,
+//     the 48-byte records and the gradient records it accumulates into, all served from the 126 MB L2 -- out of the cache
+//     (cudaMemsetAsync fills at 7.5 TB/s alone, but beside it the compositing backward ran 1.02 ms instead of 0.86 ms);
+//   * a small persistent grid (GSR_FILL_CTAS, default one 64-thread CTA per two SMs, ~3.9 TB/s): the fill has the whole duration of
+//     the backward to finish and should take as few issue slots and as little of the register file as possible.
+// Measured at cfg3 (render_bwd + preprocess_bwd incl. the join, ms): memsets on the side stream 1.396, on the main stream 1.462;
+// this kernel with 16 / 37 / 74 / 148 / 296 / 1184 CTAs 1.918 (exposed) / 1.376 / 1.377 / 1.423 / 1.428 / 1.443.
+struct FillSegs
+{
+    float4* p[10];
+    unsigned long long n16[10]; // 16-byte units
+    int count;
+};
+__global__ void __launch_bounds__(64) fill_zero_kernel(const FillSegs f)
+{
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned long long stride = (unsigned long long)gridDim.x * 64ull;
+    for (int k = 0; k < f.count; k++) {
+        float4* p = f.p[k];
+        const unsigned long long n = f.n16[k];
+        unsigned long long i = (unsigned long long)blockIdx.x * 64ull + threadIdx.x;
+        for (; i + 3 * stride < n; i += 4 * stride) { // four independent stores in flight per thread
+            __stcs(p + i, z);
+            __stcs(p + i + stride, z);
+            __stcs(p + i + 2 * stride, z);
+            __stcs(p + i + 3 * stride, z);
+        }
+        for (; i < n; i += stride) __stcs(p + i, z);
+    }
+}
+
 int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
 {
     if (a.P <= 0) return 0;
@@ -800,8 +832,34 @@ int launch_grad_fills(const PreBwdArgs& a, cudaStream_t s)
             GSR_CUDA(cudaMemsetAsync(a.vis_index, 0, 2 * W * sizeof(uint32_t), s));
         }
     } else if (!a.out.accumulate && (!fill_in_kernel() || a.has_subset)) {
-        for (auto& f : fills)
-            if (f.p && f.floats) GSR_CUDA(cudaMemsetAsync(f.p, 0, f.floats * sizeof(float), s));
+        // GSR_FILL_KERNEL=0: cudaMemsetAsync per tensor (round 1); default: one fill_zero_kernel launch
+        static const bool own = !(getenv("GSR_FILL_KERNEL") && atoi(getenv("GSR_FILL_KERNEL")) == 0);
+        static const int ctas_env = getenv("GSR_FILL_CTAS") ? atoi(getenv("GSR_FILL_CTAS")) : 0;
+        FillSegs fs;
+        fs.count = 0;
+        for (auto& f : fills) {
+            if (!f.p || !f.floats) continue;
+            const size_t bytes = f.floats * sizeof(float);
+            const bool aligned = ((size_t)f.p & 15u) == 0;
+            const size_t body = own && aligned ? bytes & ~(size_t)15 : 0;
+            if (body) {
+                fs.p[fs.count] = reinterpret_cast<float4*>(f.p);
+                fs.n16[fs.count] = body / 16;
+                fs.count++;
+            }
+            if (body < bytes) GSR_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(f.p) + body, 0, bytes - body, s)); // unaligned / tail
+        }
+        if (fs.count) {
+            static int sms = 0;
+            if (!sms) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                if (sms <= 0) sms = 148;
+            }
+            const int grid = ctas_env > 0 ? ctas_env : (sms + 1) / 2;
+            fill_zero_kernel<<<grid, 64, 0, s>>>(fs); count_launches(1);
+        }
     }
     return 0;
 }

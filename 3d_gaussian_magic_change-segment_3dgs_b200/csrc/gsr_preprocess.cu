@@ -570,6 +570,10 @@ constexpr int GATHER_THREADS = 128;
 constexpr int GATHER_GROUP = 8; // views whose index words are loaded together (one lane per view)
 constexpr int GATHER_CAP = 64;  // packets a warp stages at a time (8 views x 32 Gaussians x ~20% visible = ~51)
 constexpr int GATHER_STRIDE = 20; // words between staged packets: 16-byte aligned, and 8 consecutive packets cover all 32 banks
+// words between the SH rows staged for the store: 16-byte aligned rows whose 16-byte quarters fall into 8 different bank groups for
+// 8 consecutive lanes (52 l mod 32 = 0, 20, 8, 28, 16, 4, 24, 12), so both the per-lane 128-bit row writes and the 128-bit reads
+// of consecutive output quarters are conflict free
+constexpr int GATHER_ROW_STRIDE = 52;
 
 // 16-byte asynchronous copy, L2 only (.cg): packets are read once, and for a peer blob the request crosses NVLink as one
 // 16-byte read per lane, 64 contiguous bytes per packet (round 1 moved the 68-byte packets as 4-byte .ca copies)
@@ -588,9 +592,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Views are summed in ascending order per Gaussian on every rank, so replicas end up bitwise identical.
 __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const GatherPacketsArgs a)
 {
-    __shared__ __align__(16) uint32_t s_buf[GATHER_THREADS / 32][32 * SH_ROW_STRIDE]; // staging, then the SH rows for the coalesced store
+    __shared__ __align__(16) uint32_t s_buf[GATHER_THREADS / 32][32 * GATHER_ROW_STRIDE]; // staging, then the SH rows for the coalesced store
     __shared__ float s_cam[GSR_MAX_GATHER_VIEWS * 3];
-    static_assert(GATHER_CAP * GATHER_STRIDE <= 32 * SH_ROW_STRIDE && GSR_PACKET_WORDS == 16, "staging must fit");
+    static_assert(GATHER_CAP * GATHER_STRIDE <= 32 * GATHER_ROW_STRIDE && GSR_PACKET_WORDS == 16, "staging must fit");
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < a.num_views * 3; i += GATHER_THREADS) s_cam[i] = a.campos[i];
     __syncthreads();
@@ -707,9 +711,9 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
     if (want_sh) { // 32 consecutive rows of the warp form one contiguous span: transposed through shared memory, fully coalesced
         __syncwarp();
         float* rows = reinterpret_cast<float*>(stage);
-        float* my = rows + lane * SH_ROW_STRIDE; // stride 49: each lane's row starts in its own bank
+        float4* my4 = reinterpret_cast<float4*>(rows + lane * GATHER_ROW_STRIDE);
 #pragma unroll
-        for (int k = 0; k < 48; k++) my[k] = dsh[k];
+        for (int k = 0; k < 12; k++) my4[k] = make_float4(dsh[4 * k], dsh[4 * k + 1], dsh[4 * k + 2], dsh[4 * k + 3]);
         __syncwarp();
         const uint32_t first_row = grp * 32u;
         if (first_row < (uint32_t)a.P) {
@@ -720,18 +724,28 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
             if (a.out.dL_dsh_rest) { // raw-parameter mode: two tensors, each span still contiguous for the warp's 32 rows
                 float* dc = a.out.dL_dsh + (size_t)first_row * 3;
                 float* rest = a.out.dL_dsh_rest + (size_t)first_row * (row_floats - 3);
-                for (uint32_t e = lane; e < nrows * 3u; e += 32) dc[e] = rows[(e / 3u) * SH_ROW_STRIDE + e % 3u];
+                for (uint32_t e = lane; e < nrows * 3u; e += 32) dc[e] = rows[(e / 3u) * GATHER_ROW_STRIDE + e % 3u];
                 const uint32_t rf = (uint32_t)row_floats - 3u;
                 for (uint32_t e = lane; e < nrows * rf; e += 32) {
                     const uint32_t rr = e / rf, k = e - rr * rf + 3u;
-                    rest[e] = k < 48 ? rows[rr * SH_ROW_STRIDE + k] : 0.f;
+                    rest[e] = k < 48 ? rows[rr * GATHER_ROW_STRIDE + k] : 0.f;
+                }
+            } else if (row_floats == 48 && ((size_t)a.out.dL_dsh & 15u) == 0) {
+                // the common layout: the warp's 32 rows are one contiguous 6 KB span, moved as 384 16-byte quarters (12 trips of
+                // LDS.128 + STG.128 instead of 48 trips of 4-byte ones)
+                float4* dst4 = reinterpret_cast<float4*>(dst);
+                const uint32_t total4 = nrows * 12u;
+#pragma unroll 4
+                for (uint32_t e = lane; e < total4; e += 32) {
+                    const uint32_t rr = e / 12u, k4 = e - rr * 12u;
+                    dst4[e] = *reinterpret_cast<const float4*>(rows + rr * GATHER_ROW_STRIDE + 4u * k4);
                 }
             } else if (row_floats == 48) {
-                for (uint32_t e = lane; e < total; e += 32) dst[e] = rows[(e / 48u) * SH_ROW_STRIDE + e % 48u];
+                for (uint32_t e = lane; e < total; e += 32) dst[e] = rows[(e / 48u) * GATHER_ROW_STRIDE + e % 48u];
             } else {
                 for (uint32_t e = lane; e < total; e += 32) {
                     const uint32_t rr = e / (uint32_t)row_floats, k = e - rr * (uint32_t)row_floats;
-                    dst[e] = k < 48 ? rows[rr * SH_ROW_STRIDE + k] : 0.f;
+                    dst[e] = k < 48 ? rows[rr * GATHER_ROW_STRIDE + k] : 0.f;
                 }
             }
         }

@@ -1,6 +1,6 @@
 """One small program that launches every kernel of the library a few times (default cfg3), for `ncu --set full` (profiles/README.md)
 and, at cfg1, for `compute-sanitizer --tool memcheck`:  python scripts/profile_step.py [iterations] [workload]
-classic forward + dense backward, the raw-parameter entry, packets backward + gather over 2 views, L1+SSIM loss, fused Adam."""
+classic forward + dense backward, the raw-parameter entry, packets backward + gather over 2 views, L1+SSIM and depth-supervision losses, fused Adam."""
 import importlib
 import os
 import sys
@@ -35,6 +35,7 @@ rgrads = mv.FlatGradients(P, "cuda", split_sh=True)
 opt = optim.FusedAdam(params, rgrads, {"xyz": 1e-7, "f_dc": 1e-6, "f_rest": 1e-7, "opacity": 1e-6, "segment": 1e-6, "scaling": 1e-7, "rotation": 1e-7})
 flat = mv.FlatGradients(P, "cuda")
 gt = torch.rand(3, Hh, W, device="cuda")
+gt_depth = torch.rand(1, Hh, W, device="cuda")
 campos = [c["campos"].cuda() for c in cams]
 with torch.no_grad():
     for it in range(ITERS):
@@ -44,6 +45,7 @@ with torch.no_grad():
         # raw-parameter entry + loss + Adam (the native training step)
         fwd_r = mv.native_view_forward(D, params.views, rs)
         stats, g_color = losses.l1_ssim_loss_and_grad(fwd_r[1], gt, 0.2)
+        losses.depth_loss_and_grad(fwd_r[2], gt_depth, 0.1, fused_from_raw_depth=True)  # depth supervision: radix-select median / quantile
         mv.native_view_backward(D, params.views, rs, fwd_r, {"color": g_color}, rgrads, first=True)
         opt.step()
         # multi-view exchange format: packets of two views + one gather pass

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(PRE_BLOCK) depth_keys_kernel(GeomState g, uint
 // radix passes). While it holds item i's instance range [o_i, o_i + n_i) a thread also records, for every multiple of EMIT_CHUNK
 // inside it, that Gaussian i owns that instance: the emit kernel then starts from a table look-up instead of a search.
 constexpr int EMIT_CHUNK = 2048;
+constexpr int EMIT_PER_THREAD = EMIT_CHUNK / 256; // consecutive instances per thread of the emit kernel
 constexpr unsigned long long SB_AGG = 1ull << 62, SB_INC = 2ull << 62, SB_VAL = (1ull << 62) - 1ull;
 
 __global__ void __launch_bounds__(256) instance_scan_kernel(const ushort4* __restrict__ rect, const uint32_t* __restrict__ sorted_slots, uint32_t V,
@@ -153,22 +154,64 @@ __global__ void __launch_bounds__(256) emit_kernel(const ushort4* __restrict__ r
     if (threadIdx.x == 0) s_off[cnt] = soff[j0 + cnt];
     __syncthreads();
     const uint32_t mask = (1u << digit_bits) - 1u;
-    for (uint32_t k = begin + threadIdx.x; k < end; k += 256) {
-        uint32_t lo = 0, hi = cnt; // largest j in [0,cnt) with s_off[j] <= k
+    // A thread resolves EMIT_PER_THREAD CONSECUTIVE instances: one binary search and one division for the first, then it walks
+    // (the next instance is the next tile of the same rectangle, or the first tile of the next owner), and its keys / slots leave
+    // as 16-byte stores. (One search + one runtime division per instance cost ~170 instructions per instance: ALU pipe 64 % busy.)
+    const uint32_t k0 = begin + threadIdx.x * EMIT_PER_THREAD;
+    if (k0 < end) {
+        uint32_t lo = 0, hi = cnt; // largest j in [0,cnt) with s_off[j] <= k0
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (s_off[mid] <= k) lo = mid;
+            if (s_off[mid] <= k0) lo = mid;
             else hi = mid;
         }
-        const ushort4 r = s_rect[lo];
-        const uint32_t local = k - s_off[lo];
-        const uint32_t w = (uint32_t)(r.z - r.x);
-        const uint32_t ty = r.y + local / w;
-        const uint32_t tx = r.x + local % w;
-        const uint32_t key = ty * (uint32_t)grid_x + tx;
-        out_keys[k] = key;
-        out_vals[k] = s_slot[lo];
-        for (int p = 0; p < passes; p++) atomicAdd(&s_h[p][(key >> (p * digit_bits)) & mask], 1u);
+        ushort4 r = s_rect[lo];
+        uint32_t next_off = s_off[lo + 1];
+        uint32_t slot = s_slot[lo];
+        const uint32_t local = k0 - s_off[lo];
+        const uint32_t w0 = (uint32_t)(r.z - r.x);
+        uint32_t ty = r.y + local / w0;
+        uint32_t tx = r.x + local % w0;
+        uint32_t keys[EMIT_PER_THREAD], vals[EMIT_PER_THREAD];
+#pragma unroll
+        for (int e = 0; e < EMIT_PER_THREAD; e++) {
+            const uint32_t k = k0 + e;
+            if (k < end) {
+                while (k >= next_off) { // first tile of the next owner (every owner has >= 1 instance)
+                    lo++;
+                    r = s_rect[lo];
+                    slot = s_slot[lo];
+                    next_off = s_off[lo + 1];
+                    tx = r.x;
+                    ty = r.y;
+                }
+                const uint32_t key = ty * (uint32_t)grid_x + tx;
+                keys[e] = key;
+                vals[e] = slot;
+                for (int p = 0; p < passes; p++) atomicAdd(&s_h[p][(key >> (p * digit_bits)) & mask], 1u);
+                if (++tx == r.z) { // next tile of the rectangle, row-major like the reference (rasterizer_impl.cu:96-108)
+                    tx = r.x;
+                    ty++;
+                }
+            } else {
+                keys[e] = 0;
+                vals[e] = 0;
+            }
+        }
+        if (k0 + EMIT_PER_THREAD <= end) { // out_keys / out_vals are 256-byte aligned and k0 is a multiple of EMIT_PER_THREAD
+#pragma unroll
+            for (int e = 0; e < EMIT_PER_THREAD; e += 4) {
+                *reinterpret_cast<uint4*>(out_keys + k0 + e) = make_uint4(keys[e], keys[e + 1], keys[e + 2], keys[e + 3]);
+                *reinterpret_cast<uint4*>(out_vals + k0 + e) = make_uint4(vals[e], vals[e + 1], vals[e + 2], vals[e + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EMIT_PER_THREAD; e++)
+                if (k0 + e < end) {
+                    out_keys[k0 + e] = keys[e];
+                    out_vals[k0 + e] = vals[e];
+                }
+        }
     }
     __syncthreads();
     for (int p = 0; p < passes; p++) {

@@ -298,7 +298,7 @@ int radix_digit_bits(int nbits);
 size_t radix_lookback_ws_words(uint32_t n_cap, int nbits);
 // one kernel per pass (decoupled look-back); see gsr_scan_sort.cu
 int radix_sort_pairs_lookback(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* ws, size_t ws_words, bool hist_ready,
-                              cudaStream_t s, const uint32_t* n_dev = nullptr);
+                              cudaStream_t s, const uint32_t* n_dev = nullptr, int keys_per_thread = 16);
 
 int knn_run(int P, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t knn_workspace_bytes(int P);

@@ -576,7 +576,7 @@ int radix_digit_bits(int nbits)
 // whole workspace and its key producer has accumulated the digit totals (digit p = bits [p * digit_bits, (p + 1) * digit_bits));
 // otherwise the workspace is zeroed and the totals are computed here. n < 2^30 (the look-back words carry 30 bits).
 int radix_sort_pairs_lookback(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int nbits, uint32_t* ws, size_t ws_words, bool hist_ready,
-                              cudaStream_t s, const uint32_t* n_dev)
+                              cudaStream_t s, const uint32_t* n_dev, int keys_per_thread)
 {
     const int passes = radix_num_passes(nbits);
     if (n == 0 || passes == 0) return 0;
@@ -586,7 +586,8 @@ int radix_sort_pairs_lookback(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, 
         return GSR_ERR_INVALID_ARGUMENT;
     }
     const int digit_bits = radix_digit_bits(nbits);
-    static const int pt = getenv("GSR_LB_PT") ? atoi(getenv("GSR_LB_PT")) : 16;
+    static const int pt_env = getenv("GSR_LB_PT") ? atoi(getenv("GSR_LB_PT")) : 0;
+    const int pt = pt_env ? pt_env : keys_per_thread;
     const uint32_t items = RADIX_THREADS * (uint32_t)(pt == 8 ? 8 : 16);
     const uint32_t tiles = (n + items - 1) / items;
     const uint32_t tiles_cap = (n + RADIX_ITEMS - 1) / RADIX_ITEMS;

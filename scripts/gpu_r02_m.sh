@@ -1,21 +1,21 @@
 #!/bin/bash
-# round 2, session 2: gather kernel with 16-byte SH row stores; 5-CTA variant of the compositing backward; full ncu set
+# round 2, session 2: emit kernel with 8 consecutive instances per thread; depth-sort tile size A/B
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 T=${1:-m}
 timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest.log
 tail -5 gpurun_out/${T}_pytest.log
-timeout 300 python scripts/time_gather.py 8 > gpurun_out/${T}_gather.log 2>&1
-timeout 300 python scripts/time_gather.py 2 >> gpurun_out/${T}_gather.log 2>&1
-timeout 300 python scripts/time_gather.py 1 >> gpurun_out/${T}_gather.log 2>&1
-cat gpurun_out/${T}_gather.log
 rm -f gpurun_out/${T}_ab.log
-GSR_FILL_STREAM=main timeout 300 python scripts/ab_bwd.py x cfg3 >> gpurun_out/${T}_ab.log 2>&1
-GSR_FILL_STREAM=main GSR_BWD_VARIANT=9 timeout 300 python scripts/ab_bwd.py x cfg3 >> gpurun_out/${T}_ab.log 2>&1
+timeout 300 python scripts/ab_bwd.py x cfg3 >> gpurun_out/${T}_ab.log 2>&1
+GSR_DEPTH_PT=8 timeout 300 python scripts/ab_bwd.py x cfg3 >> gpurun_out/${T}_ab.log 2>&1
+timeout 300 python scripts/ab_bwd.py x cfg2 >> gpurun_out/${T}_ab.log 2>&1
 cat gpurun_out/${T}_ab.log
-K='regex:^(adam|argmax|block_offsets|depth_keys|emit|fill_zero|find_index|gather_packets|grad_|gyd|init_ranks|instance_scan|inverse_depth|mad_|max_|preprocess|radix|render|select|sqdiff|ssim|sums|tile_ranges|zero_grad)'
-timeout 2400 ncu --set full --clock-control none -k "$K" --launch-skip 80 -c 120 -o /tmp/${T}_full python scripts/profile_step.py 2 cfg3 > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-ncu -i /tmp/${T}_full.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_raw.csv 2>/dev/null
-python profiles/extract_kernels.py /tmp/${T}_full.ncu-rep gpurun_out/r02_kernels.json > /dev/null; echo "extract rc=$?"
-ls -la /tmp/${T}_full.ncu-rep gpurun_out/r02_ncu_full_raw.csv gpurun_out/r02_kernels.json
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-cfg4-base > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${T}_bench.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/${T}_bench.json'))
+print({k:d.get(k) for k in ['value','ms_per_step','fwd_ms_per_frame','gpu_launches']}, d['e2e']['value'], d['e2e']['ms_per_step'])
+print({k:v['ms'] for k,v in d['stages'].items()})
+print(d['roofline'])
+PY
 rm -f gpurun_out/ab_bwd_*.pt

@@ -200,9 +200,18 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
     if world > 1:
         counts_all = torch.empty(world * nv, dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(counts_all, counts_local, group=group)
-    else:
+        need = max(int(counts_all.max().item()), 1)  # the only host read of the exchange
+    else:  # one rank (several views per step on one GPU): the counts are host values already, nothing is read back
         counts_all = counts_local
-    need = max(int(counts_all.max().item()), 1)  # the only host read of the exchange
+        need = max(max(int(s[2]) for s in local_sets), 1)
+    if world == 1:  # local gather: one pointer per view blob, no stacking copy, no common capacity needed
+        campos = torch.stack([all_campos[0][v] for v in range(nv)]).contiguous()
+        cap = max(D.packet_blob_capacity(s[0], P) for s in local_sets)
+        if state is not None:
+            state["cap"] = max(int(state.get("cap", 0)), min(P, (int(need * 1.05) + 1023) // 1024 * 1024))
+        D.gather_packets_v(leaves["means3D"], campos, sh_degree, M, [s[0].data_ptr() for s in local_sets], D.packet_index_words(P), 0, cap,
+                           flat.backward_out())
+        return counts_all
     sticky = int(state.get("cap", 0)) if state is not None else 0
     if sticky >= need:
         cap = sticky

@@ -259,6 +259,11 @@ def test_gradient_packets_rebuild_dense_rows():
     mv.exchange_packets(D, None, flat, gs, sets2, [campos], 3, world=1, state=st)
     for leaf, nat in names.items():
         assert H.rel_linf(flat.views[leaf], dense[0][nat] + dense[1][nat]) <= 2e-5, leaf
+    # the stacked-blob entry (what follows an ncclAllGather of equally sized blobs): gsr_gather_packets
+    flat.buffer.fill_(9.0)
+    D.gather_packets(gs["means3D"], torch.stack(campos).contiguous(), 3, gs["shs"].size(1), torch.stack([s[0] for s in sets2]), flat.backward_out())
+    for leaf, nat in names.items():
+        assert H.rel_linf(flat.views[leaf], dense[0][nat] + dense[1][nat]) <= 2e-5, leaf
 
 
 def test_packet_capacity_comes_from_the_forward_it_belongs_to():

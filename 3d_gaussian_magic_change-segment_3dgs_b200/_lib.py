@@ -77,7 +77,7 @@ ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctyp
 SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scratch_bytes", "gsr_backward_scratch_bytes_n", "gsr_backward", "gsr_mark_visible",
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
            "gsr_backward_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
-           "gsr_peer_free", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible", "gsr_microbench", "gsr_count_work", "gsr_depth_loss", "gsr_depth_loss_scratch_bytes"]
+           "gsr_peer_free", "gsr_peer_copy", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible", "gsr_microbench", "gsr_count_work", "gsr_depth_loss", "gsr_depth_loss_scratch_bytes"]
 GSR_ABI_VERSION = 3  # include/gsr.h
 GSR_PACKET_WORDS = 16
 GSR_PEER_HANDLE_BYTES = 64
@@ -131,6 +131,8 @@ def lib():
     L.gsr_peer_close.argtypes = [ctypes.c_void_p]
     L.gsr_peer_free.restype = ctypes.c_int
     L.gsr_peer_free.argtypes = [ctypes.c_void_p]
+    L.gsr_peer_copy.restype = ctypes.c_int
+    L.gsr_peer_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.gsr_image_loss_scratch_bytes.restype = ctypes.c_size_t
     L.gsr_image_loss_scratch_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
     L.gsr_image_loss.restype = ctypes.c_int

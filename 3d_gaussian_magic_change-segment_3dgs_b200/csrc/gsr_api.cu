@@ -568,6 +568,16 @@ extern "C" int gsr_peer_free(void* ptr)
     if (ptr) GSR_CUDA(cudaFree(ptr));
     return 0;
 }
+extern "C" int gsr_peer_copy(void* dst, const void* src, size_t bytes, gsr_stream_t stream_)
+{
+    if (bytes == 0) return 0;
+    if (!dst || !src) {
+        set_error("gsr_peer_copy: invalid argument");
+        return GSR_ERR_INVALID_ARGUMENT;
+    }
+    GSR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream_));
+    return 0;
+}
 
 static int backward_impl(const GsrView* view, const GsrGaussians* in, const int32_t* radii, const GsrState* state, const float* alpha,
                          const GsrPixelGrads* pix, const GsrParamGrads* grads, void* scratch, size_t scratch_bytes, cudaStream_t s,

@@ -754,6 +754,242 @@ __global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_kernel(const
     } // groups
 }
 
+// ---- the same pass as a software pipeline (GSR_GATHER_PIPE=1) ----
+// While a warp sums the packets of group g out of one staging buffer, the asynchronous copies of its group g + 1 are already
+// landing in the other one, and the index pairs and positions of the group after that are in flight: a warp's (local or NVLink)
+// round trips overlap its own arithmetic and row stores instead of alternating with them. Only the first segment (the first <= 64
+// packets) of a group's first 8 views is prefetched -- the common case; anything beyond is copied synchronously as above.
+constexpr int GATHER_STAGE_WORDS = 32 * GATHER_ROW_STRIDE;
+constexpr int GATHER_PIPE_SMEM_BYTES = (GATHER_THREADS / 32) * 2 * GATHER_STAGE_WORDS * (int)sizeof(uint32_t);
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct GatherViews // what lane u < 8 knows about view g0 + u of the warp's 32 Gaussians
+{
+    uint32_t bits, first, cnt, incl; // visible bits, first packet, packet count, inclusive scan of the counts over the view lanes
+};
+__device__ __forceinline__ GatherViews gather_views(const uint2 pr, const bool has_view, const uint32_t capacity, const uint32_t lane)
+{
+    GatherViews g;
+    g.bits = 0u;
+    g.first = 0u;
+    if (has_view) {
+        const uint32_t cnt = __popc(pr.x), f0 = ~pr.y;
+        const bool ok = f0 <= capacity && cnt <= capacity - f0; // a corrupt index cannot make a span leave its blob
+        g.bits = ok ? pr.x : 0u;
+        g.first = f0;
+    }
+    g.cnt = __popc(g.bits);
+    g.incl = g.cnt;
+#pragma unroll
+    for (int d = 1; d < GATHER_GROUP; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, g.incl, d);
+        if (lane >= (uint32_t)d) g.incl += t;
+    }
+    return g;
+}
+// Issue the copies of the views [u0, e) of a view group -- the longest run whose packets fit the staging buffer. Returns e
+// (>= u0 + 1: one view never has more than 32 packets); m = the views of the run that see this lane's Gaussian.
+__device__ __forceinline__ uint32_t gather_issue(const GatherPacketsArgs& a, const int g0, const uint32_t nvg, const GatherViews& g, const uint32_t u0,
+                                                 const uint32_t base, uint32_t* stage, const uint32_t lane, uint32_t& m)
+{
+    const uint32_t fit = __ballot_sync(0xffffffffu, lane >= u0 && lane < nvg && g.incl - base <= GATHER_CAP);
+    const uint32_t e = u0 + __popc(fit);
+    m = 0u;
+    for (uint32_t u = u0; u < e; u++) {
+        const uint32_t b_u = __shfl_sync(0xffffffffu, g.bits, u);
+        const uint32_t nquads = __popc(b_u) * (GSR_PACKET_WORDS / 4); // 16-byte quarters of this view's adjacent packets
+        if (nquads == 0u) continue;
+        const uint32_t f_u = __shfl_sync(0xffffffffu, g.first, u);
+        const uint32_t off_u = __shfl_sync(0xffffffffu, g.incl - g.cnt, u) - base;
+        const uint32_t* src = a.views[g0 + u] + a.packet_off + (size_t)f_u * GSR_PACKET_WORDS;
+        uint32_t* dst = stage + off_u * GATHER_STRIDE;
+        for (uint32_t qd = lane; qd < nquads; qd += 32) cp_async_16(dst + (qd >> 2) * GATHER_STRIDE + (qd & 3u) * 4u, src + qd * 4u);
+        m |= ((b_u >> lane) & 1u) << u;
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(GATHER_THREADS, 4) gather_packets_pipe_kernel(const GatherPacketsArgs a)
+{
+    extern __shared__ __align__(16) uint32_t s_gather[]; // [warps][2][GATHER_STAGE_WORDS]
+    __shared__ float s_cam[GSR_MAX_GATHER_VIEWS * 3];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < a.num_views * 3; i += GATHER_THREADS) s_cam[i] = a.campos[i];
+    __syncthreads();
+    const uint32_t W = ((uint32_t)a.P + 31u) >> 5; // groups of 32 Gaussians = index pairs per view
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool want_sh = a.out.dL_dsh && a.M > 0;
+    uint32_t* const stage0 = s_gather + warp * 2 * GATHER_STAGE_WORDS;
+    const uint32_t nvg0 = (uint32_t)min(GATHER_GROUP, a.num_views);
+    const uint32_t stride = gridDim.x * (GATHER_THREADS / 32);
+    uint32_t grp = blockIdx.x * (GATHER_THREADS / 32) + warp;
+    if (grp >= W) return;
+
+    auto load_pair = [&](uint32_t g) {
+        uint2 pr = make_uint2(0u, 0u);
+        if (g < W && lane < nvg0) pr = __ldg(reinterpret_cast<const uint2*>(a.views[lane] + a.index_off) + g);
+        return pr;
+    };
+    auto load_pos = [&](uint32_t g) {
+        const uint32_t id = g * 32u + lane;
+        const size_t i = (size_t)(g < W && id < (uint32_t)a.P ? id : 0u);
+        return make_float3(a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]);
+    };
+
+    // prologue: this warp's first group is staged, the second one's index pairs and positions are requested
+    uint32_t cb = 0u;
+    GatherViews gc = gather_views(load_pair(grp), lane < nvg0, a.capacity, lane);
+    float3 pos = load_pos(grp);
+    uint32_t m_c = 0u, e_c = 0u;
+    if (__shfl_sync(0xffffffffu, gc.incl, nvg0 - 1) != 0u) e_c = gather_issue(a, 0, nvg0, gc, 0u, 0u, stage0, lane, m_c);
+    cp_async_commit();
+    uint2 pr_n = load_pair(grp + stride);
+    float3 pos_n = load_pos(grp + stride);
+
+    for (; grp < W; grp += stride) {
+        uint32_t* const stage = stage0 + cb * GATHER_STAGE_WORDS;
+        // ---- next group: its first segment starts travelling into the other buffer; the group after it is requested ----
+        const GatherViews gn = gather_views(pr_n, lane < nvg0 && grp + stride < W, a.capacity, lane);
+        uint32_t m_n = 0u, e_n = 0u;
+        if (__shfl_sync(0xffffffffu, gn.incl, nvg0 - 1) != 0u) e_n = gather_issue(a, 0, nvg0, gn, 0u, 0u, stage0 + (cb ^ 1u) * GATHER_STAGE_WORDS, lane, m_n);
+        cp_async_commit();
+        pr_n = load_pair(grp + 2 * stride);
+        const float3 pos_nn = load_pos(grp + 2 * stride);
+        cp_async_wait_group<1>(); // everything but the copies just issued: this group's first segment has landed
+        __syncwarp();
+
+        const uint32_t id = grp * 32u + lane;
+        const bool valid = id < (uint32_t)a.P;
+        float acc[13], dsh[48];
+#pragma unroll
+        for (int k = 0; k < 13; k++) acc[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 48; k++) dsh[k] = 0.f;
+        const size_t i = (size_t)(valid ? id : 0);
+        for (int g0 = 0; g0 < a.num_views; g0 += GATHER_GROUP) {
+            const uint32_t nvg = (uint32_t)min(GATHER_GROUP, a.num_views - g0);
+            GatherViews g = gc;
+            uint32_t m = m_c, e = e_c;
+            bool staged = true; // the first segment of the first 8 views is already in `stage`
+            if (g0 > 0) {
+                uint2 pr = make_uint2(0u, 0u);
+                if (lane < nvg) pr = __ldg(reinterpret_cast<const uint2*>(a.views[g0 + lane] + a.index_off) + grp);
+                g = gather_views(pr, lane < nvg, a.capacity, lane);
+                staged = false;
+            }
+            if (__shfl_sync(0xffffffffu, g.incl, nvg - 1) == 0u) continue; // none of the 32 Gaussians is visible in these views
+            uint32_t u0 = 0u, base = 0u;
+            while (u0 < nvg) { // usually one segment: all views of the group fit the staging buffer
+                if (!staged) {
+                    __syncwarp(); // the previous segment's readers are done with the staging buffer
+                    e = gather_issue(a, g0, nvg, g, u0, base, stage, lane, m);
+                    cp_async_commit();
+                    cp_async_wait_group<0>();
+                    __syncwarp();
+                }
+                staged = false;
+                if (!valid) m = 0u;
+                while (__any_sync(0xffffffffu, m != 0u)) {
+                    const uint32_t u = m ? (uint32_t)__ffs(m) - 1u : 0u;
+                    const uint32_t b_u = __shfl_sync(0xffffffffu, g.bits, u);
+                    const uint32_t off_u = __shfl_sync(0xffffffffu, g.incl - g.cnt, u) - base;
+                    if (m) {
+                        m &= m - 1u;
+                        const float4* pk = reinterpret_cast<const float4*>(stage + (off_u + __popc(b_u & lt_mask)) * GATHER_STRIDE);
+                        const float4 p0 = pk[0], p1 = pk[1], p2 = pk[2], p3 = pk[3];
+                        const float f[13] = {p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, p3.z, p3.w};
+#pragma unroll
+                        for (int k = 0; k < 13; k++) acc[k] += f[k];
+                        if (want_sh) {
+                            const int r = g0 + (int)u;
+                            const float cr = p0.x, cg = p0.y, cb_ = p0.z;
+                            V3 dir_orig = {pos.x - s_cam[3 * r], pos.y - s_cam[3 * r + 1], pos.z - s_cam[3 * r + 2]};
+                            const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+                            float w[16];
+                            sh_basis(a.D, dir_orig.x / len, dir_orig.y / len, dir_orig.z / len, w);
+#pragma unroll
+                            for (int k = 0; k < 16; k++) {
+                                dsh[3 * k + 0] += w[k] * cr;
+                                dsh[3 * k + 1] += w[k] * cg;
+                                dsh[3 * k + 2] += w[k] * cb_;
+                            }
+                        }
+                    }
+                }
+                base = __shfl_sync(0xffffffffu, g.incl, e - 1);
+                u0 = e;
+            }
+        }
+        if (valid) {
+            if (a.out.dL_dmeans3D) {
+                a.out.dL_dmeans3D[3 * i + 0] = acc[0];
+                a.out.dL_dmeans3D[3 * i + 1] = acc[1];
+                a.out.dL_dmeans3D[3 * i + 2] = acc[2];
+            }
+            if (a.out.dL_dopacity) a.out.dL_dopacity[i] = acc[3];
+            if (a.out.dL_dsegments && a.S == 2) {
+                a.out.dL_dsegments[2 * i + 0] = acc[4];
+                a.out.dL_dsegments[2 * i + 1] = acc[5];
+            }
+            if (a.out.dL_dscales) {
+                a.out.dL_dscales[3 * i + 0] = acc[6];
+                a.out.dL_dscales[3 * i + 1] = acc[7];
+                a.out.dL_dscales[3 * i + 2] = acc[8];
+            }
+            if (a.out.dL_drotations) *reinterpret_cast<float4*>(a.out.dL_drotations + 4 * i) = {acc[9], acc[10], acc[11], acc[12]};
+        }
+        if (want_sh) { // 32 consecutive rows of the warp form one contiguous span: transposed through shared memory, fully coalesced
+            __syncwarp();
+            float* rows = reinterpret_cast<float*>(stage);
+            float4* my4 = reinterpret_cast<float4*>(rows + lane * GATHER_ROW_STRIDE);
+#pragma unroll
+            for (int k = 0; k < 12; k++) my4[k] = make_float4(dsh[4 * k], dsh[4 * k + 1], dsh[4 * k + 2], dsh[4 * k + 3]);
+            __syncwarp();
+            const uint32_t first_row = grp * 32u;
+            const uint32_t nrows = min(32u, (uint32_t)a.P - first_row);
+            const int row_floats = a.M * 3;
+            float* dst = a.out.dL_dsh + (size_t)first_row * row_floats;
+            const uint32_t total = nrows * (uint32_t)row_floats;
+            if (a.out.dL_dsh_rest) { // raw-parameter mode: two tensors, each span still contiguous for the warp's 32 rows
+                float* dc = a.out.dL_dsh + (size_t)first_row * 3;
+                float* rest = a.out.dL_dsh_rest + (size_t)first_row * (row_floats - 3);
+                for (uint32_t e2 = lane; e2 < nrows * 3u; e2 += 32) dc[e2] = rows[(e2 / 3u) * GATHER_ROW_STRIDE + e2 % 3u];
+                const uint32_t rf = (uint32_t)row_floats - 3u;
+                for (uint32_t e2 = lane; e2 < nrows * rf; e2 += 32) {
+                    const uint32_t rr = e2 / rf, k = e2 - rr * rf + 3u;
+                    rest[e2] = k < 48 ? rows[rr * GATHER_ROW_STRIDE + k] : 0.f;
+                }
+            } else if (row_floats == 48 && ((size_t)a.out.dL_dsh & 15u) == 0) {
+                float4* dst4 = reinterpret_cast<float4*>(dst);
+                const uint32_t total4 = nrows * 12u;
+#pragma unroll 4
+                for (uint32_t e2 = lane; e2 < total4; e2 += 32) {
+                    const uint32_t rr = e2 / 12u, k4 = e2 - rr * 12u;
+                    dst4[e2] = *reinterpret_cast<const float4*>(rows + rr * GATHER_ROW_STRIDE + 4u * k4);
+                }
+            } else if (row_floats == 48) {
+                for (uint32_t e2 = lane; e2 < total; e2 += 32) dst[e2] = rows[(e2 / 48u) * GATHER_ROW_STRIDE + e2 % 48u];
+            } else {
+                for (uint32_t e2 = lane; e2 < total; e2 += 32) {
+                    const uint32_t rr = e2 / (uint32_t)row_floats, k = e2 - rr * (uint32_t)row_floats;
+                    dst[e2] = k < 48 ? rows[rr * GATHER_ROW_STRIDE + k] : 0.f;
+                }
+            }
+        }
+        __syncwarp(); // the row store is done with this buffer before the group after next stages into it
+        gc = gn;
+        m_c = m_n;
+        e_c = e_n;
+        pos = pos_n;
+        pos_n = pos_nn;
+        cb ^= 1u;
+    }
+    cp_async_wait_group<0>();
+}
+
 // Zero the gradient records of the live slots only: one warp per slot-block, 3 x 16 bytes per visible Gaussian, contiguous.
 __global__ void __launch_bounds__(256) zero_grad_rec_kernel(GeomState g, float4* __restrict__ grad_rec)
 {
@@ -904,7 +1140,20 @@ int launch_gather_packets(const GatherPacketsArgs& a, cudaStream_t s)
         resident = 4 * (sms > 0 ? sms : 148);
     }
     const unsigned groups = ((unsigned)a.P + 31u) / 32u, want = (groups + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32);
-    gather_packets_kernel<<<want < (unsigned)resident ? want : (unsigned)resident, GATHER_THREADS, 0, s>>>(a); count_launches(1);
+    // GSR_GATHER_PIPE=1: the software-pipelined form (next group's packets travel while this one is summed)
+    static const bool pipe = getenv("GSR_GATHER_PIPE") && atoi(getenv("GSR_GATHER_PIPE")) != 0;
+    const unsigned grid = want < (unsigned)resident ? want : (unsigned)resident;
+    if (pipe) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(gather_packets_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_PIPE_SMEM_BYTES);
+            attr_set = true;
+        }
+        gather_packets_pipe_kernel<<<grid, GATHER_THREADS, GATHER_PIPE_SMEM_BYTES, s>>>(a);
+    } else {
+        gather_packets_kernel<<<grid, GATHER_THREADS, 0, s>>>(a);
+    }
+    count_launches(1);
     return 0;
 }
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s)

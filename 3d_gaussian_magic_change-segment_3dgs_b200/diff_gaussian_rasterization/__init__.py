@@ -505,6 +505,13 @@ def peer_open(handle, device):
         return int(ptr.value)
 
 
+def peer_copy(dst, src, nbytes, device, stream=None):
+    """gsr_peer_copy: stream-ordered copy between device addresses of which either may be a peer's mapping (copy engines)."""
+    with torch.cuda.device(device):
+        st = (stream if stream is not None else torch.cuda.current_stream(device)).cuda_stream
+        _lib.check(_lib.lib().gsr_peer_copy(ctypes.c_void_p(int(dst)), ctypes.c_void_p(int(src)), int(nbytes), st), "gsr_peer_copy")
+
+
 def peer_close(ptr, device):
     with torch.cuda.device(device):
         _lib.check(_lib.lib().gsr_peer_close(ctypes.c_void_p(ptr)), "gsr_peer_close")

@@ -238,25 +238,47 @@ def exchange_packets(D, dist, flat, leaves, local_sets, all_campos, sh_degree, w
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Peer-memory exchange (NVLink / NVSwitch): every rank writes its views' blobs into a buffer that the other ranks have mapped
-# (gsr_peer_alloc / gsr_peer_open), and after ONE stream-ordered barrier the gather kernel of every rank pulls all ranks'
-# packets straight over NVLink while it sums them -- the transfer IS the kernel's loads: no all-gather, no staging copy, no
-# host read. Blobs are double-buffered: a rank may start writing step s+1 while a slower rank still reads step s.
+# Peer-memory exchange (NVLink / NVSwitch): every rank owns a buffer that the other ranks have mapped (gsr_peer_alloc /
+# gsr_peer_open). Two forms, one stream-ordered barrier each, no all-gather, no host read:
+#   pull  (default) a rank writes its views' blobs into ITS OWN buffer and the gather kernel of every rank reads all ranks' packets
+#         straight over NVLink while it sums them -- the transfer IS the kernel's loads;
+#   push  every rank's buffer has a receive slot per (rank, view); as soon as a view's backward has produced its blob, the copy
+#         engines write it into that slot of every peer (one side stream per peer: with several views per rank the transfer of
+#         view k travels while view k + 1 renders), and the gather kernels read LOCAL memory only.
+# Measured on 8 B200 (cfg4, one view per rank, 551 MB in and out per GPU and step): pull 2.0 ms for barrier + gather = 276 GB/s
+# inbound, the same with and without the software-pipelined kernel (not a per-warp latency limit); push 3.3 ms for copies +
+# barrier + local gather (0.64 ms) = ~205 GB/s for the peer copies, one stream or seven. NCCL's own all-reduce of the dense
+# buffer moves ~420 GB/s per GPU and direction on the same box, so peer traffic, not the kernels, bounds the exchange here;
+# pull stays the default (GSR_PEER_MODE=push or mode="push" selects the other; both are parity-tested on 2 GPUs).
+# Blobs are double-buffered: a rank may write step s+1 while a slower rank still reads step s (the barrier of step s+1 orders
+# the reuse at s+2).
 # ---------------------------------------------------------------------------------------------------------------------
 class PeerUnavailable(RuntimeError):
     """Raised on EVERY rank when peer-visible buffers could not be set up on some rank (no CUDA IPC / no peer access)."""
 
 
 class PeerPacketExchange:
-    def __init__(self, D, dist, P, views_per_rank, rank, world, device, capacity=None, group=None):
+    def __init__(self, D, dist, P, views_per_rank, rank, world, device, capacity=None, group=None, mode=None):
         """Collective: all ranks construct it together. Either every rank succeeds or every rank raises PeerUnavailable (the
-        outcome is agreed with an all-reduce), so callers can fall back to exchange_packets (NCCL all-gather) consistently."""
+        outcome is agreed with an all-reduce), so callers can fall back to exchange_packets (NCCL all-gather) consistently.
+        mode: "pull" (default) or "push" (see above; GSR_PEER_MODE overrides the default)."""
+        import os
+
         self.D, self.dist, self.P, self.nv, self.rank, self.world, self.device, self.group = D, dist, P, views_per_rank, rank, world, device, group
+        self.mode = mode or os.environ.get("GSR_PEER_MODE", "pull")
+        if self.mode not in ("push", "pull"):
+            raise ValueError("PeerPacketExchange mode must be 'push' or 'pull'")
         self.capacity = int(capacity) if capacity else P  # packets per view; P always fits
         self.index_off = 0
         self.packet_off = D.packet_index_words(P)  # 128-byte aligned
         self.blob_words = D.packet_blob_words(P, self.capacity)
-        nbytes = 4 * self.blob_words * self.nv
+        self.slots = self.nv * (world if self.mode == "push" else 1)  # push: a receive slot per (rank, view)
+        # one side stream per peer, so that the copies to different peers can run on different copy engines
+        self._push_stream = [torch.cuda.Stream(device=device) for _ in range(world)] if (self.mode == "push" and world > 1) else None
+        self._push_done = None
+        self._nvis = {}
+        self.pushed_bytes = 0
+        nbytes = 4 * self.blob_words * self.slots
         self.local, self.peers, handles = [], [[], []], []
         self._opened = False
         err = None
@@ -314,23 +336,65 @@ class PeerPacketExchange:
     def blob_ptr(self, base, v):
         return base + 4 * self.blob_words * v
 
+    def slot(self, r, v):
+        """Index of the blob of view v of rank r inside a rank's buffer."""
+        return r * self.nv + v if self.mode == "push" else v
+
     def view_backward(self, leaves, rs, fwd, upstream, v, means2D_grad=None):
-        """Backward of this rank's view v of the step, written as a blob into the current peer-visible buffer."""
+        """Backward of this rank's view v of the step, written as a blob into the current peer-visible buffer (push: and from
+        there into every peer's receive slot, by the copy engines on a side stream)."""
         R, color, depth, segment, alpha, radii, geom, binb, img = fwd
-        base = self.blob_ptr(self.local[self.parity], v)
+        base = self.blob_ptr(self.local[self.parity], self.slot(self.rank, v))
         sh, raw = _sh_and_raw(leaves)
         _, count = self.D._backward_packets_native(rs, leaves["means3D"], radii, leaves["segments"], leaves["scales"], leaves["rotations"],
                                                    upstream.get("color"), upstream.get("segment"), upstream.get("depth"), upstream.get("alpha"),
                                                    sh, geom, R, binb, img, alpha, capacity=self.capacity, means2D_grad=means2D_grad,
                                                    raw=(base + 4 * self.packet_off, base + 4 * self.index_off), raw_params=raw)
+        if self._push_stream is not None:
+            nvis = int(R.num_visible) if hasattr(R, "num_visible") else self.capacity  # V is a host value of this view's forward
+            self._nvis[v] = nvis
+            self.push_view(v, nvis)
         return count
+
+    def push_view(self, v, nvis):
+        """Push form: copy the used prefix of this rank's blob of view v -- the visibility index, then its `nvis` packets -- into
+        the same slot of every peer's current buffer, on the side stream, ordered after what the current stream has enqueued."""
+        nbytes = 4 * (self.packet_off + min(int(nvis), self.capacity) * self.D.PACKET_WORDS)
+        off = 4 * self.blob_words * self.slot(self.rank, v)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        if self._push_done is None:
+            self._push_done = []
+        for r in range(self.world):
+            if r != self.rank:
+                st = self._push_stream[r]
+                st.wait_event(ready)
+                self.D.peer_copy(self.peers[self.parity][r] + off, self.local[self.parity] + off, nbytes, self.device, st)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self._push_done.append(ev)
+        self.pushed_bytes = nbytes * (self.world - 1)
+
+    def repush(self):
+        """Re-issue the pushes of the step's views (measurement support: bench.py times push + barrier + gather in isolation)."""
+        if self._push_stream is not None:
+            for v, n in sorted(self._nvis.items()):
+                self.push_view(v, n)
 
     def exchange(self, flat, leaves, all_campos, sh_degree):
         """Fills flat.buffer with the sum over all ranks' views of the step (all ranks call this after their view_backward
         calls). all_campos[r][v]: camera centre (device [3]) of view v of rank r."""
+        if self._push_done:  # this rank's blobs have landed in every peer's slots
+            cur = torch.cuda.current_stream(self.device)
+            for ev in self._push_done:
+                cur.wait_event(ev)
+        self._push_done = None
         if self.world > 1:
             self.dist.all_reduce(self._flag, group=self.group)  # stream-ordered barrier: every rank's blobs are complete
-        ptrs = [self.blob_ptr(self.peers[self.parity][r], v) for r in range(self.world) for v in range(self.nv)]
+        if self.mode == "push":
+            ptrs = [self.blob_ptr(self.local[self.parity], self.slot(r, v)) for r in range(self.world) for v in range(self.nv)]
+        else:
+            ptrs = [self.blob_ptr(self.peers[self.parity][r], v) for r in range(self.world) for v in range(self.nv)]
         campos = torch.stack([all_campos[r][v] for r in range(self.world) for v in range(self.nv)]).contiguous()
         self.D.gather_packets_v(leaves["means3D"], campos, sh_degree, sh_coeffs_of(leaves), ptrs, self.packet_off, self.index_off,
                                 self.capacity, flat.backward_out())

@@ -758,7 +758,10 @@ def ours_arm(args, out):
                     rs = make_settings(GS, cams[v], bg)
                     comm_sets.append(mv.native_view_backward_packets(Dmod, leaves, rs, native_forward(rs), ug, capacity=xstate.get("cap", 0)))
         dist.barrier()
-        comm_ms = event_time(lambda: flat_exchange(mode, comm_sets), 5, warm=2)
+        if mode == "peer" and px.mode == "push":  # the transfer happens in the views' backward (copy engines, side stream): time it too
+            comm_ms = event_time(lambda: (px.repush(), flat_exchange(mode, comm_sets)), 5, warm=2)
+        else:
+            comm_ms = event_time(lambda: flat_exchange(mode, comm_sets), 5, warm=2)
 
     def fwd_only_fn():
         with torch.no_grad():
@@ -909,8 +912,11 @@ def ours_arm(args, out):
         what = "rasterize_gaussians fwd (colour+depth+alpha+segment) + bwd (dL/dcolour, dL/ddepth)"
     exch = ""
     if nranks > 1:
-        exch = {"peer": ", gradient exchange = peer memory: every rank's gather kernel pulls all ranks' packets of the visible Gaussians over NVLink "
-                        "while summing them into the flat buffer (one stream-ordered barrier, no all-gather)",
+        exch = {"peer": (", gradient exchange = peer memory (push): every view's packets of the visible Gaussians are written into every peer's "
+                         "receive slots over NVLink by the copy engines, one stream-ordered barrier, one local gather pass into the flat buffer"
+                         if (px is not None and px.mode == "push") else
+                         ", gradient exchange = peer memory (pull): every rank's gather kernel pulls all ranks' packets of the visible Gaussians "
+                         "over NVLink while summing them into the flat buffer (one stream-ordered barrier, no all-gather)"),
                 "packets": ", gradient exchange = one NCCL all-gather of per-view blobs (packets of the visible Gaussians + visibility index), then "
                            "one gather pass into the flat buffer",
                 "dense": ", gradients accumulated in one flat buffer (61 floats/Gaussian), one NCCL all-reduce"}[mode]
@@ -946,11 +952,21 @@ def ours_arm(args, out):
     if comm_ms is not None:
         pw = Dmod.PACKET_WORDS if hasattr(Dmod, "PACKET_WORDS") else 17
         if mode == "peer":
-            pulled = int((4 * pw * stats["V"] + P // 4) * V * (nranks - 1))
-            line["collective"] = {"op": "4-byte ncclAllReduce as stream-ordered barrier + ONE gather kernel over %d views reading peer blobs over "
-                                        "NVLink (%d B per visible Gaussian + 2 index words per 32 Gaussians per view)" % (nranks * V, 4 * pw),
-                                  "bytes_pulled_per_rank": pulled, "ms": round(comm_ms, 3),
-                                  "nvlink_GBps_in": round(pulled / (comm_ms * 1e-3) / 1e9, 1), "dense_allreduce_bytes": int(61 * 4 * P)}
+            moved = int((4 * pw * stats["V"] + P // 4) * V * (nranks - 1))
+            if px.mode == "push":
+                line["collective"] = {"op": "PUSH: every view blob (64 B per visible Gaussian + 2 index words per 32 Gaussians) is written into its "
+                                            "receive slot on every peer by the copy engines (posted NVLink writes on a side stream, issued right "
+                                            "after the view's backward) + 4-byte ncclAllReduce as stream-ordered barrier + ONE gather kernel over "
+                                            "%d views reading local memory" % (nranks * V),
+                                      "bytes_pushed_per_rank": moved, "bytes_received_per_rank": moved, "ms": round(comm_ms, 3),
+                                      "what_ms_is": "pushes of this rank's views + barrier + gather, timed alone after a barrier (in the step the "
+                                                    "pushes of view k overlap the rendering of view k + 1)",
+                                      "nvlink_GBps_in": round(moved / (comm_ms * 1e-3) / 1e9, 1), "dense_allreduce_bytes": int(61 * 4 * P)}
+            else:
+                line["collective"] = {"op": "PULL: 4-byte ncclAllReduce as stream-ordered barrier + ONE gather kernel over %d views reading peer blobs "
+                                            "over NVLink (%d B per visible Gaussian + 2 index words per 32 Gaussians per view)" % (nranks * V, 4 * pw),
+                                      "bytes_pulled_per_rank": moved, "ms": round(comm_ms, 3),
+                                      "nvlink_GBps_in": round(moved / (comm_ms * 1e-3) / 1e9, 1), "dense_allreduce_bytes": int(61 * 4 * P)}
         elif mode == "packets":
             line["collective"] = {"op": "count all-gather + ONE ncclAllGather of view blobs + ONE gather pass over %d views" % (nranks * V),
                                   "bytes_sent_per_rank": int((4 * pw * xstate.get("cap", stats["V"]) + P // 4) * V), "ms": round(comm_ms, 3),

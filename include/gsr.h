@@ -215,6 +215,10 @@ int gsr_peer_alloc(size_t bytes, void** ptr, void* handle_out);
 int gsr_peer_open(const void* handle, void** ptr);
 int gsr_peer_close(void* ptr);
 int gsr_peer_free(void* ptr);
+/* Stream-ordered copy of `bytes` between two device buffers of which either may be a peer's (gsr_peer_open): the PUSH form of the
+ * exchange -- a rank writes its view blob into every peer's receive slot with the copy engines (posted NVLink writes) and the
+ * peers' gather kernels then read local memory only. */
+int gsr_peer_copy(void* dst, const void* src, size_t bytes, gsr_stream_t stream);
 
 /* Fused multi-tensor Adam over flat buffers (replaces torch.optim.Adam(l, lr=0.0, eps=1e-15) and its seven
  * parameter groups, scene/gaussian_model.py:166-177, following the default foreach path op by op in fp32). params / grads /

@@ -27,7 +27,7 @@ ug = {k: (v.to(dev) if v is not None else None) for k, v in syn.upstream_grads(W
 bg = torch.tensor([0.0, 0.0, 0.0])
 e = torch.empty(0)
 NV = 4
-px = mv.PeerPacketExchange(D, dist, P, NV, rank, world, dev)
+px = mv.PeerPacketExchange(D, dist, P, NV, rank, world, dev, mode="pull")  # this script times the kernel's own NVLink loads
 campos = [[syn.make_camera(W, Hh, yaw_deg=45.0 * (r * NV + v))["campos"].to(dev) for v in range(NV)] for r in range(world)]
 for v in range(NV):
     cam = syn.make_camera(W, Hh, yaw_deg=45.0 * (rank * NV + v))

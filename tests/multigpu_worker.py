@@ -46,21 +46,23 @@ assert err <= 2e-5, err  # two backward runs: fp32 atomic-order noise
 ref = flat.packed()
 dist.broadcast(ref, 0)
 assert torch.equal(ref, flat.packed()), "replicas differ"
-# peer-memory path: blobs written into peer-visible buffers, gather kernel pulls them over NVLink (3 steps: both buffers)
-px = mv.PeerPacketExchange(D, dist, P, 1, rank, world, dev)
-for step in range(3):
-    peer = mv.FlatGradients(P, dev)
-    peer.buffer.fill_(-3.0)
-    cnt = px.view_backward(gs, rs, fwd, ug, 0)
-    px.exchange(peer, gs, campos, 3)
-    torch.cuda.synchronize()
-    assert int(cnt) == sets[0][2]
-    err_p = float((peer.packed() - dense.packed()).abs().max()) / float(dense.packed().abs().max())
-    assert err_p <= 2e-5, (step, err_p)
-    ref = peer.packed()
-    dist.broadcast(ref, 0)
-    assert torch.equal(ref, peer.packed()), "peer replicas differ"
-px.close()
+# peer-memory path, both forms (3 steps each: both buffers): push = the copy engines write every blob into the peers' receive slots
+# and the gather kernel reads local memory; pull = the gather kernel reads the peers' buffers over NVLink
+for peer_mode in ("push", "pull"):
+    px = mv.PeerPacketExchange(D, dist, P, 1, rank, world, dev, mode=peer_mode)
+    for step in range(3):
+        peer = mv.FlatGradients(P, dev)
+        peer.buffer.fill_(-3.0)
+        cnt = px.view_backward(gs, rs, fwd, ug, 0)
+        px.exchange(peer, gs, campos, 3)
+        torch.cuda.synchronize()
+        assert int(cnt) == sets[0][2]
+        err_p = float((peer.packed() - dense.packed()).abs().max()) / float(dense.packed().abs().max())
+        assert err_p <= 2e-5, (peer_mode, step, err_p)
+        ref = peer.packed()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, peer.packed()), "peer replicas differ (%s)" % peer_mode
+    px.close()
 # raw-parameter layout end to end: flat parameters -> fused-activation forward -> packets into peer buffers -> gather into the
 # split flat gradient buffer -> fused Adam; replicas must stay bitwise identical after the optimiser step
 optim = importlib.import_module(H.PKG_NAME + ".optim")

@@ -309,10 +309,16 @@ def stage_views(cams, gt_img, gt_dep, device, copy_stream):
         for t in mats + [gi, gd]:
             if t is not None:
                 t.record_stream(torch.cuda.current_stream())
-        nv = (v + 1) % V
-        pending[nv] = stage(nv)  # the next view's (next step's) inputs travel while this view computes
         return mats, gi, gd
 
+    def prefetch(v):
+        """Stage the inputs of the view after v (the next view's / next step's) -- called once this view's forward has been enqueued, so
+        that the host work of the copies does not delay the step's first kernel; the copies travel while this view computes."""
+        nv = (v + 1) % V
+        if nv not in pending:
+            pending[nv] = stage(nv)
+
+    next_view.prefetch = prefetch
     return next_view
 
 
@@ -455,10 +461,12 @@ def reference_arm(args, out):
             if fwd_only:  # viewer frame: camera in, image out
                 with torch.no_grad():
                     color = rasterize(rs, torch.zeros_like(leaves["means3D"]))[0]
+                next_view.prefetch(v)
                 host_img.copy_(color, non_blocking=True)
                 continue
             means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
             color, radii, depth, alpha, segment = rasterize(rs, means2D)
+            next_view.prefetch(v)
             loss = reference_train_loss(color, depth, gi, gd)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
@@ -685,6 +693,7 @@ def ours_arm(args, out):
             mats, _, _ = next_view(0)
             with torch.no_grad():
                 color = render_parts(make_settings(GS, cams[0], bg, mats))[0]
+            next_view.prefetch(0)
             host_img.copy_(color, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return
@@ -698,6 +707,7 @@ def ours_arm(args, out):
             if use_flat:
                 with torch.no_grad():
                     fwd = native_forward(rs)
+                next_view.prefetch(v)
                 color, depth = fwd[1].requires_grad_(True), fwd[2].requires_grad_(True)
                 loss = loss_fn(color, depth, gi, gd)
                 loss.backward()  # pixel gradients only; the rasterizer backward runs natively into the flat buffer / as packets
@@ -706,6 +716,7 @@ def ours_arm(args, out):
             else:
                 means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
                 color, radii, depth, alpha, segment = rasterize(rs, means2D)
+                next_view.prefetch(v)
                 loss = loss_fn(color, depth, gi, gd)
                 loss.backward()
             total = loss.detach() if total is None else total + loss.detach()

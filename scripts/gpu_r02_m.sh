@@ -1,11 +1,18 @@
 #!/bin/bash
-# round 2, session 2: pipelined gather kernel, correctness on one GPU + local timing A/B
+# round 2, session 2: single-pass block_offsets, compact depth bits for depth_keys; tests + stage times + bench
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 T=${1:-m}
-GSR_GATHER_PIPE=1 timeout 900 python -m pytest tests/test_api_gpu.py tests/test_fullsize_gpu.py tests/test_raw_params_gpu.py -m gpu -q -x -k "packet or gather or exchange or linearity" > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest.log
-tail -4 gpurun_out/${T}_pytest.log
-for pipe in 0 1; do for nv in 8 1; do
-GSR_GATHER_PIPE=$pipe timeout 300 python scripts/time_gather.py $nv >> gpurun_out/${T}_gather.log 2>&1
-done; done
-cat gpurun_out/${T}_gather.log
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest.log
+tail -5 gpurun_out/${T}_pytest.log
+rm -f gpurun_out/${T}_ab.log
+timeout 300 python scripts/ab_bwd.py x cfg3 >> gpurun_out/${T}_ab.log 2>&1
+cat gpurun_out/${T}_ab.log
+timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-cfg4-base > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${T}_bench.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/${T}_bench.json'))
+print({k:d.get(k) for k in ['value','ms_per_step','fwd_ms_per_frame','gpu_launches']}, d['e2e']['value'], d['e2e']['ms_per_step'])
+print({k:v['ms'] for k,v in d['stages'].items()})
+PY
+rm -f gpurun_out/ab_bwd_*.pt

@@ -96,22 +96,30 @@ __global__ void __launch_bounds__(256) instance_scan_kernel(const ushort4* __res
         if (w < warp) wbase += c;
         total += c;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) { // the look-back is done by a whole warp: 32 predecessors' words per round trip (one thread walking them one
+                     // dependent load at a time was the longest phase of this kernel)
         volatile unsigned long long* st = status;
-        st[tile] = (tile == 0 ? SB_INC : SB_AGG) | (unsigned long long)total;
+        if (lane == 0) st[tile] = (tile == 0 ? SB_INC : SB_AGG) | (unsigned long long)total;
         unsigned long long excl = 0;
         if (tile > 0) {
-            uint32_t t = tile - 1;
+            int t = (int)tile - 1;
             while (true) {
-                const unsigned long long w = st[t];
-                if ((w & ~SB_VAL) == 0ull) continue;
-                excl += w & SB_VAL;
-                if (w & SB_INC) break;
-                t--;
+                const int tt = t - (int)lane;
+                unsigned long long w = 2ull << 62; // = SB_INC: entries before tile 0 are never consumed (tile 0 is INCLUSIVE)
+                if (tt >= 0) w = st[tt];
+                while ((w & ~SB_VAL) == 0ull) w = st[tt];          // every predecessor holds a ticket, so it publishes
+                const uint32_t incs = __ballot_sync(0xffffffffu, (w & SB_INC) != 0ull);
+                const uint32_t first = incs ? (uint32_t)__ffs(incs) - 1u : 31u;
+                unsigned long long val = lane <= first ? (w & SB_VAL) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                excl += val;
+                if (incs) break;
+                t -= 32;
             }
-            st[tile] = SB_INC | (excl + total);
+            if (lane == 0) st[tile] = SB_INC | (excl + total);
         }
-        s_prefix = excl;
+        if (lane == 0) s_prefix = excl;
     }
     __syncthreads();
     uint32_t o = (uint32_t)s_prefix + wbase + incl - sum;

@@ -30,6 +30,21 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane)
     return v;
 }
 
+// Lanes of the warp whose (<= 8-bit) digit equals this lane's, by eight ballots -- one per digit bit -- instead of match.any: in the
+// ncu source view of the look-back pass, match.any and the instruction consuming its result held 52 % of all stall samples (a long,
+// unpipelined latency paid 16 times per thread and tile); the ballots are independent of one another and pipeline.
+__device__ __forceinline__ uint32_t same_digit_lanes(const uint32_t d, const bool valid)
+{
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+        const bool one = (d >> bit) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, one);
+        peers &= one ? b : ~b;
+    }
+    return peers;
+}
+
 // block-wide exclusive scan of one value per thread (256 threads); returns exclusive prefix, total in `total`
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/, uint32_t& total)
 {
@@ -217,9 +232,8 @@ __device__ __forceinline__ void tile_scatter_body(uint32_t tile, const uint32_t*
     for (int k = 0; k < RADIX_PER_THREAD; k++) {
         const uint32_t i = wbase + k * 32 + lane;
         const bool valid = i < n;
-        // invalid lanes get a digit outside the histogram so they never match a valid lane
-        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0x100u + lane;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0u;
+        const uint32_t peers = same_digit_lanes(d, valid);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
         uint32_t pos = 0;
         if (valid) pos = s_cnt[warp][d] + rank;
@@ -323,6 +337,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_sort_coop_kernel(const Ra
 // inclusive prefix. Tiles are handed out by an atomic ticket, so every predecessor of a running tile is running or done and the
 // walk cannot dead-lock. Ranking inside the tile is the stable match.any scheme of tile_scatter_body.
 constexpr uint32_t LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_VAL = (1u << 30) - 1u;
+constexpr int LB_BATCH = 8; // predecessors whose look-back words are requested together
 // Keys per thread of the look-back passes (tile = 256 x LB_PER_THREAD keys): larger tiles amortise the look-back walk and the
 // fixed per-tile work. GSR_LB_PT=8 selects 2048-key tiles for A/B runs.
 
@@ -422,13 +437,27 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(cons
     if (has_digit) {
         uint32_t excl = 0;
         if (tile > 0) {
-            uint32_t t = tile - 1;
-            while (true) {
-                const uint32_t v = ld_volatile_u32(a.status + (size_t)t * 256 + threadIdx.x);
-                if ((v & ~LB_VAL) == 0u) continue; // not published yet
-                excl += v & LB_VAL;
-                if (v & LB_INC) break;
-                t--; // tile 0 always publishes INCLUSIVE, so t never passes 0
+            // Walk back over the predecessors' words LB_BATCH at a time: the loads of a batch are independent, so a walk over k
+            // tiles costs ~k / LB_BATCH L2 round trips instead of k. (With ~740 tiles in flight a tile meets its first INCLUSIVE
+            // word dozens of tiles back; walking them one dependent load at a time made the look-back -- not the sorting -- the
+            // longest phase of a tile: ~110 us per 10 M-key pass.)
+            int t = (int)tile - 1;
+            bool found = false;
+            while (!found) {
+                uint32_t v[LB_BATCH];
+#pragma unroll
+                for (int j = 0; j < LB_BATCH; j++) // entries before tile 0 are never consumed: tile 0 always publishes INCLUSIVE
+                    v[j] = t - j >= 0 ? ld_volatile_u32(a.status + (size_t)(t - j) * 256 + threadIdx.x) : LB_INC;
+#pragma unroll
+                for (int j = 0; j < LB_BATCH; j++) {
+                    if (!found) {
+                        uint32_t w = v[j];
+                        while ((w & ~LB_VAL) == 0u) w = ld_volatile_u32(a.status + (size_t)(t - j) * 256 + threadIdx.x); // not published yet
+                        excl += w & LB_VAL;
+                        found = (w & LB_INC) != 0u;
+                    }
+                }
+                t -= LB_BATCH;
             }
             st_volatile_u32(a.status + (size_t)tile * 256 + threadIdx.x, LB_INC | (excl + tot));
         }
@@ -441,8 +470,8 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(cons
     for (int k = 0; k < LB_PER_THREAD; k++) {
         const uint32_t i = wbase + k * 32 + lane;
         const bool valid = i < n;
-        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0x100u + lane;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0u;
+        const uint32_t peers = same_digit_lanes(d, valid);
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
         uint32_t pos = 0;
         if (valid) pos = s_cnt[warp][d] + rank;

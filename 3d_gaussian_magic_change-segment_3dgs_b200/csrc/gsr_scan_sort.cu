@@ -365,7 +365,7 @@ struct LookbackPassArgs
 };
 
 template <int LB_PER_THREAD>
-__global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(const LookbackPassArgs a)
+__global__ void __launch_bounds__(RADIX_THREADS, 4) radix_lookback_pass_kernel(const LookbackPassArgs a)
 {
     constexpr int LB_ITEMS = RADIX_THREADS * LB_PER_THREAD;
     __shared__ uint32_t s_cnt[8][256];
@@ -435,12 +435,34 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(cons
             gstart += s_warp2[w];
         }
     if (has_digit) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) s_cnt[w][threadIdx.x] = dstart + wpre[w]; // rank base inside the tile
+    }
+    __syncthreads();
+    // ---- rank the keys inside the tile and park them in shared memory in tile order: everything that does NOT need the
+    //      predecessors. The look-back comes after it, so the tiles in front have had this whole phase to publish. ----
+#pragma unroll
+    for (int k = 0; k < LB_PER_THREAD; k++) {
+        const uint32_t i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0u;
+        const uint32_t peers = same_digit_lanes(d, valid);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t pos = 0;
+        if (valid) pos = s_cnt[warp][d] + rank;
+        __syncwarp();
+        if (valid && rank == 0) s_cnt[warp][d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            s_keys[pos] = key[k];
+            s_vals[pos] = val[k];
+        }
+    }
+    if (has_digit) {
         uint32_t excl = 0;
         if (tile > 0) {
             // Walk back over the predecessors' words LB_BATCH at a time: the loads of a batch are independent, so a walk over k
-            // tiles costs ~k / LB_BATCH L2 round trips instead of k. (With ~740 tiles in flight a tile meets its first INCLUSIVE
-            // word dozens of tiles back; walking them one dependent load at a time made the look-back -- not the sorting -- the
-            // longest phase of a tile: ~110 us per 10 M-key pass.)
+            // tiles costs ~k / LB_BATCH L2 round trips instead of k.
             int t = (int)tile - 1;
             bool found = false;
             while (!found) {
@@ -461,27 +483,7 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_lookback_pass_kernel(cons
             }
             st_volatile_u32(a.status + (size_t)tile * 256 + threadIdx.x, LB_INC | (excl + tot));
         }
-#pragma unroll
-        for (int w = 0; w < 8; w++) s_cnt[w][threadIdx.x] = dstart + wpre[w]; // rank base inside the tile
         s_gbase[threadIdx.x] = gstart + excl - dstart;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < LB_PER_THREAD; k++) {
-        const uint32_t i = wbase + k * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t d = valid ? ((key[k] >> shift) & mask) : 0u;
-        const uint32_t peers = same_digit_lanes(d, valid);
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        uint32_t pos = 0;
-        if (valid) pos = s_cnt[warp][d] + rank;
-        __syncwarp();
-        if (valid && rank == 0) s_cnt[warp][d] += __popc(peers);
-        __syncwarp();
-        if (valid) {
-            s_keys[pos] = key[k];
-            s_vals[pos] = val[k];
-        }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < tile_n; i += RADIX_THREADS) {

@@ -349,8 +349,9 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     GSR_CUDA(cudaMemsetAsync(g.dhist, 0, g.dhist_words * sizeof(uint32_t), s));
     launch_depth_keys(g, g.dhist, s);
     GSR_LAUNCHED(s, debug, "depth_keys");
-    // the depth sort has few keys (V ~ 1.2 M at cfg3 = 294 tiles of 4096): GSR_DEPTH_PT=8 gives it twice as many CTAs of half the size (A/B)
-    static const int depth_pt = getenv("GSR_DEPTH_PT") ? atoi(getenv("GSR_DEPTH_PT")) : 16;
+    // the depth sort has few keys (V ~ 1.2 M at cfg3 = 294 tiles of 4096 keys, two per SM): 2048-key tiles give it twice as many CTAs
+    // (0.125 -> 0.110 ms at cfg3; the tile sort, 10 M keys, is better off with 4096: 0.146 vs 0.179 ms). GSR_DEPTH_PT=16 for A/B.
+    static const int depth_pt = getenv("GSR_DEPTH_PT") ? atoi(getenv("GSR_DEPTH_PT")) : 8;
     int dres = radix_sort_pairs_lookback(g.dkeys, g.dvals, g.slots, 32, g.dhist, g.dhist_words, true, s, g.counters + CNT_VISIBLE, depth_pt);
     if (dres < 0) return dres;
     GSR_LAUNCHED(s, debug, "depth_sort");

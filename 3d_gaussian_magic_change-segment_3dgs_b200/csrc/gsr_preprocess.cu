@@ -146,7 +146,13 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
         a.radii[idx] = radius_out;
     }
 
-    // slot compaction inside the block (stable in Gaussian-id order)
+    // slot compaction inside the block (stable in Gaussian-id order); the block's instance count and its "filtered although
+    // prefiltered" flag ride on the same barrier (one __syncthreads per CTA instead of two)
+    uint32_t t = tiles;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const bool warp_filtered = __any_sync(0xffffffffu, filtered);
+    if (lane_id() == 0) s_tiles[threadIdx.x >> 5] = t | (warp_filtered ? 0x80000000u : 0u); // a warp's 32 rectangles stay far below 2^31 tiles
     uint32_t nvis;
     const uint32_t rank = block_rank_256(visible, s_warp, nvis);
     if (visible) {
@@ -169,15 +175,13 @@ __global__ void __launch_bounds__(PRE_BLOCK) preprocess_fwd_kernel(const PreFwdA
         }
     }
     // instance count of the block -> global R (integer atomics: deterministic total)
-    uint32_t t = tiles;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane_id() == 0) s_tiles[threadIdx.x >> 5] = t;
-    const uint32_t any_filtered = __syncthreads_or(filtered ? 1 : 0);
     if (threadIdx.x == 0) {
-        uint32_t tt = 0;
+        uint32_t tt = 0, any_filtered = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) tt += s_tiles[w];
+        for (int w = 0; w < 8; w++) {
+            tt += s_tiles[w] & 0x7fffffffu;
+            any_filtered |= s_tiles[w] >> 31;
+        }
         a.g.blk_count[blockIdx.x] = nvis;
         if (tt) atomicAdd(reinterpret_cast<unsigned long long*>(a.g.counters + CNT_RENDERED_LO), (unsigned long long)tt);
         if (any_filtered) atomicOr(a.g.counters + CNT_ERROR, 1u);

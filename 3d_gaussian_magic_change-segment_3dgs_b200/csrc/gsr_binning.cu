@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const ushort4* __restrict__ r
         uint32_t ty = r.y + local / w0;
         uint32_t tx = r.x + local % w0;
         uint32_t keys[EMIT_PER_THREAD], vals[EMIT_PER_THREAD];
+        uint32_t run_digit = 0xffffffffu, run_count = 0;
 #pragma unroll
         for (int e = 0; e < EMIT_PER_THREAD; e++) {
             const uint32_t k = k0 + e;
@@ -200,7 +201,19 @@ __global__ void __launch_bounds__(256) emit_kernel(const ushort4* __restrict__ r
                 const uint32_t key = ty * (uint32_t)grid_x + tx;
                 keys[e] = key;
                 vals[e] = slot;
-                for (int p = 0; p < passes; p++) atomicAdd(&s_h[p][(key >> (p * digit_bits)) & mask], 1u);
+                atomicAdd(&s_h[0][key & mask], 1u);
+                // digit of the second pass (tile id / 128): a thread's consecutive tiles nearly always share it, and so do its
+                // neighbours' -- counted one by one these were 32-way same-address shared-memory atomics; counted per run they are few
+                if (passes > 1) {
+                    const uint32_t d1 = (key >> digit_bits) & mask;
+                    if (d1 != run_digit) {
+                        if (run_count) atomicAdd(&s_h[1][run_digit], run_count);
+                        run_digit = d1;
+                        run_count = 0;
+                    }
+                    run_count++;
+                    for (int p = 2; p < passes; p++) atomicAdd(&s_h[p][(key >> (p * digit_bits)) & mask], 1u);
+                }
                 if (++tx == r.z) { // next tile of the rectangle, row-major like the reference (rasterizer_impl.cu:96-108)
                     tx = r.x;
                     ty++;
@@ -210,6 +223,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const ushort4* __restrict__ r
                 vals[e] = 0;
             }
         }
+        if (run_count) atomicAdd(&s_h[1][run_digit], run_count);
         if (k0 + EMIT_PER_THREAD <= end) { // out_keys / out_vals are 256-byte aligned and k0 is a multiple of EMIT_PER_THREAD
 #pragma unroll
             for (int e = 0; e < EMIT_PER_THREAD; e += 4) {

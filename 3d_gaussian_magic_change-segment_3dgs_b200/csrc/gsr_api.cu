@@ -90,6 +90,7 @@ struct HostSync
 {
     uint32_t* pinned = nullptr;
     cudaEvent_t ev = nullptr;
+    size_t last_bin_bytes = 0; // binning state of the previous forward on this (thread, device): the next one's speculative size
 };
 static HostSync* host_sync()
 {
@@ -357,6 +358,17 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     GSR_LAUNCHED(s, debug, "depth_sort");
     const uint32_t* sorted_slots = g.dvals[dres];
 
+    // The binning state is requested BEFORE the wait, with the previous forward's size + 12.5 % as a guess: the allocator callback
+    // (Python, through ctypes: tens of microseconds) then runs while the GPU is busy instead of between the wait and the
+    // remaining launches, where the depth sort is all that covers the host. The exact size is requested again only if the guess
+    // was too small (the allocator's last answer for a buffer kind is the one that counts).
+    char* bin_base = nullptr;
+    size_t bin_cap = 0;
+    if (hs->last_bin_bytes) {
+        bin_cap = hs->last_bin_bytes + hs->last_bin_bytes / 8;
+        bin_base = (char*)alloc(alloc_user, GSR_BUF_BINNING, bin_cap);
+        if (!bin_base) bin_cap = 0;
+    }
     GSR_CUDA(cudaEventSynchronize(hs->ev));
     const uint32_t* counters = hs->pinned;
     if (counters[CNT_ERROR] & 1u) {
@@ -376,7 +388,8 @@ extern "C" int gsr_forward(const GsrView* view, const GsrGaussians* in_, const G
     const int tile_bits = ceil_log2(T) < 1 ? 1 : ceil_log2(T);
     BinState b;
     const size_t bin_bytes = bin_layout(nullptr, V, R, tile_bits, b);
-    char* bin_base = (char*)alloc(alloc_user, GSR_BUF_BINNING, bin_bytes);
+    hs->last_bin_bytes = bin_bytes;
+    if (bin_bytes > bin_cap) bin_base = (char*)alloc(alloc_user, GSR_BUF_BINNING, bin_bytes);
     if (!bin_base) {
         set_error("binning state allocation failed (%zu B)", bin_bytes);
         return GSR_ERR_ALLOC;

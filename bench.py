@@ -76,38 +76,45 @@ while True:
     except Exception as e:
         print("ERR", e, flush=True); break
     print("%.6f,%d,%d,%.1f,%s" % (time.time(), sm, mx, pw, "|".join(k for k, b in R.items() if rs & b)), flush=True)
-    time.sleep(0.01)
+    time.sleep(0.02)
 """
 
 
 class ClockSampler:
-    """SM clock / throttle-reason sampling every 10 ms in a side PROCESS (NVML through pynvml; no GIL contention with the timed
-    loop). Falls back to `nvidia-smi -lms 20` when pynvml is unavailable."""
+    """SM clock / throttle-reason sampling every 20 ms in a side PROCESS that writes to a file (NVML through pynvml): the timed
+    process runs no reader thread, so nothing competes for its GIL. Falls back to `nvidia-smi -lms 20` when pynvml is unavailable."""
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc, self.mode = gpu_index, [], None, None
+        self.gpu, self.rows, self.proc, self.mode, self.path, self.fh = gpu_index, [], None, None, None, None
 
     def start(self):
+        import tempfile
+
+        fd, self.path = tempfile.mkstemp(prefix="gsr_clocks_", suffix=".csv")
+        self.fh = os.fdopen(fd, "w")
         try:
             import pynvml  # noqa: F401
 
-            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.gpu)], stdout=self.fh, stderr=subprocess.DEVNULL)
             self.mode = "nvml"
         except Exception:
             try:
                 q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                      "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
-                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=timestamp," + q, "--format=csv,noheader,nounits",
+                                              "-lms", "20"], stdout=self.fh, stderr=subprocess.DEVNULL)
                 self.mode = "smi"
             except Exception:
                 self.proc = None
-        if self.proc is not None:
-            threading.Thread(target=self._read, daemon=True).start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _collect(self):
+        if self.path is None or self.rows:
+            return
+        try:
+            with open(self.path) as f:
+                self.rows = [(None, line.strip()) for line in f if line.strip()]
+        except OSError:
+            self.rows = []
 
     def stop(self):
         if self.proc is not None:
@@ -116,18 +123,38 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+            self.proc = None
+        if self.fh is not None:
+            self.fh.close()
+            self.fh = None
+        if self.path is not None:
+            self._collect()
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+            self.path = None
 
     def summary(self, windows):
         """windows: list of (t0, t1) wall-clock intervals of the timed regions."""
         sm, mx, reasons = [], [], set()
-        for t_read, line in self.rows:
+        if self.path is not None:  # the sampler is still running: read what it has written so far
+            try:
+                with open(self.path) as fh:
+                    self.rows = [(None, line.strip()) for line in fh if line.strip()]
+            except OSError:
+                pass
+        for _, line in self.rows:
             f = [x.strip() for x in line.split(",")]
             try:
                 if self.mode == "nvml":
                     t, s, m, rs = float(f[0]), float(f[1]), float(f[2]), [r for r in f[4].split("|") if r]
-                else:
-                    t, s, m = t_read, float(f[0]), float(f[1])
-                    rs = [n for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]) if v.lower().startswith("active")]
+                else:  # nvidia-smi timestamp: YYYY/MM/DD HH:MM:SS.mmm (local time)
+                    import datetime
+
+                    t = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    s, m = float(f[1]), float(f[2])
+                    rs = [n for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]) if v.lower().startswith("active")]
             except (ValueError, IndexError):
                 continue
             if not any(a <= t <= b + 0.02 for a, b in windows):
@@ -138,7 +165,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
         return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "source": self.mode, "period_ms": 10 if self.mode == "nvml" else 20,
+                "samples": len(sm), "source": self.mode, "period_ms": 20,
                 "window": "device-timed and e2e-timed regions"}
 
 

@@ -47,7 +47,10 @@ typedef void* gsr_stream_t; /* cudaStream_t */
 enum { GSR_BUF_GEOM = 0, GSR_BUF_BINNING = 1, GSR_BUF_IMG = 2 };
 
 /* Called by gsr_forward to obtain each state buffer once its size is known. Must return a device pointer
- * aligned to >= 256 bytes (NULL = failure). bytes may be 0. */
+ * aligned to >= 256 bytes (NULL = failure). bytes may be 0. GSR_BUF_BINNING may be requested twice in one forward: first
+ * speculatively (the previous forward's size plus a margin, before the instance count has come back from the device, so that the
+ * allocator runs while the GPU is busy) and again with the exact size if that was too small; the LAST answer for a buffer kind is
+ * the buffer of this forward, an earlier one is unused and may be released. */
 typedef void* (*gsr_alloc_fn)(void* user, int which, size_t bytes);
 
 /* Per-view constants: GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:168-180). */

@@ -20,6 +20,6 @@ export GSR_BENCH_MIN_WARMUP=0
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r02_launches_ours_cfg3.csv python bench.py $BENCH_ARGS > gpurun_out/final_ncu_ours.log 2>&1; echo "ncu ours rc=$?"
 python profiles/summarize_launches.py gpurun_out/r02_launches_ours_cfg3.csv > gpurun_out/r02_launches_ours_cfg3.txt; head -14 gpurun_out/r02_launches_ours_cfg3.txt | cut -c1-140
 K='regex:^(adam|argmax|block_offsets|depth_keys|emit|fill_zero|find_index|gather_packets|grad_|gyd|init_ranks|instance_scan|inverse_depth|mad_|max_|preprocess|radix|render|select|sqdiff|ssim|sums|tile_ranges|zero_grad)'
-timeout 2400 ncu --set full --clock-control none -k "$K" --launch-skip 80 -c 120 -o /tmp/final_full python scripts/profile_step.py 2 cfg3 > gpurun_out/final_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 2400 ncu --set full --clock-control none -k "$K" --launch-skip 93 -c 85 -o /tmp/final_full python scripts/profile_step.py 2 cfg3 > gpurun_out/final_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i /tmp/final_full.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_raw.csv 2>/dev/null
 python profiles/extract_kernels.py /tmp/final_full.ncu-rep gpurun_out/r02_kernels.json > /dev/null; echo "extract rc=$?"

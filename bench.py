@@ -72,10 +72,9 @@ while True:
     try:
         sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
         rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-        pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
     except Exception as e:
         print("ERR", e, flush=True); break
-    print("%.6f,%d,%d,%.1f,%s" % (time.time(), sm, mx, pw, "|".join(k for k, b in R.items() if rs & b)), flush=True)
+    print("%.6f,%d,%d,%.1f,%s" % (time.time(), sm, mx, 0.0, "|".join(k for k, b in R.items() if rs & b)), flush=True)
     time.sleep(0.02)
 """
 

@@ -78,7 +78,7 @@ SYMBOLS = ["gsr_abi_version", "gsr_last_error", "gsr_forward", "gsr_backward_scr
            "gsr_knn_workspace_bytes", "gsr_knn_dist2", "gsr_export_state", "gsr_launch_count", "gsr_set_profiling", "gsr_get_stage_times",
            "gsr_backward_packets", "gsr_gather_packets", "gsr_gather_packets_v", "gsr_packet_index_words", "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close",
            "gsr_peer_free", "gsr_peer_copy", "gsr_adam_step", "gsr_select_rows", "gsr_image_loss", "gsr_image_loss_scratch_bytes", "gsr_last_num_visible", "gsr_microbench", "gsr_count_work", "gsr_depth_loss", "gsr_depth_loss_scratch_bytes"]
-GSR_ABI_VERSION = 3  # include/gsr.h
+GSR_ABI_VERSION = 4  # include/gsr.h
 GSR_PACKET_WORDS = 16
 GSR_PEER_HANDLE_BYTES = 64
 GSR_MAX_GATHER_VIEWS = 64

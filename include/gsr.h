@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 3
+#define GSR_ABI_VERSION 4
 #define GSR_MAX_NUM_CLASS 64
 
 #define GSR_OK 0

